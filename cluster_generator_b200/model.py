@@ -1,0 +1,318 @@
+"""
+Cluster model: radial tables + the particle-generation API.
+
+Drop-in mirror of the particle-path part of ``cluster_generator.model.ClusterModel``:
+constructors ``from_arrays`` (model.py:129-146), ``no_gas`` (:620-656),
+``from_dens_and_temp`` (:474-523), ``from_dens_and_tden`` (:565-618), the shared
+``_from_scratch`` (:213-269), the lazy ``dm_virial / star_virial`` (:111-127),
+``check_hse / check_dm_virial / check_star_virial`` (:667-716) and
+``generate_{dm,star,gas,tracer}_particles`` (:766-1039) with the reference
+signatures.  Table construction (N ~ 1000 ``quad`` calls) stays on
+the host with the reference's own scipy calls; everything per-particle and the
+f(E) build run in CUDA.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import numpy as np
+import torch
+from scipy.integrate import cumulative_trapezoid as cumtrapz
+from scipy.integrate import quad
+from scipy.interpolate import InterpolatedUnivariateSpline
+
+from . import _native as N
+from .particles import ClusterParticles
+from .utils import G, integrate, integrate_mass, keV, mp, mu, mue, mylog, parse_prng, seed_from_prng, unit_array
+from .virial import (PRIVATE_TRIAL_SEED, DeviceSpline, SamplerDiagnostics, SamplerTables,
+                     VirialEquilibrium, _out_code, radius_cdf_table, shard_bounds)
+
+_UNITS = {
+    "radius": "kpc", "density": "Msun/kpc**3", "total_density": "Msun/kpc**3",
+    "dark_matter_density": "Msun/kpc**3", "stellar_density": "Msun/kpc**3",
+    "total_mass": "Msun", "gas_mass": "Msun", "dark_matter_mass": "Msun", "stellar_mass": "Msun",
+    "temperature": "keV", "pressure": "Msun/(Myr**2*kpc)", "gravitational_field": "kpc/Myr**2",
+    "gravitational_potential": "kpc**2/Myr**2", "gas_fraction": "",
+}
+
+
+def _tag(fields):
+    for k in list(fields.keys()):
+        fields[k] = unit_array(fields[k], _UNITS.get(k, getattr(fields[k], "units", "")))
+    return fields
+
+
+class ClusterModel:
+    default_fields = [
+        "density", "temperature", "pressure", "total_density", "gravitational_potential",
+        "gravitational_field", "total_mass", "gas_mass", "dark_matter_mass", "dark_matter_density",
+        "stellar_density", "stellar_mass",
+    ]
+
+    def __init__(self, num_elements, fields):
+        self.num_elements = int(num_elements)
+        self.fields = _tag(fields)
+        self._dm_virial = None
+        self._star_virial = None
+        self._gas_tables = {}
+
+    # -- virial models (model.py:111-127) ------------------------------------
+    @property
+    def dm_virial(self) -> VirialEquilibrium:
+        if self._dm_virial is None:
+            self._dm_virial = VirialEquilibrium(self, "dark_matter")
+        return self._dm_virial
+
+    @property
+    def star_virial(self) -> VirialEquilibrium:
+        if self._star_virial is None and "stellar_density" in self:
+            self._star_virial = VirialEquilibrium(self, "stellar")
+        return self._star_virial
+
+    # -- construction --------------------------------------------------------
+    @classmethod
+    def from_arrays(cls, fields):
+        return cls(np.asarray(fields["radius"]).size, OrderedDict(fields))
+
+    @classmethod
+    def _from_scratch(cls, fields, stellar_density=None):
+        """model.py:213-269"""
+        rr = np.asarray(fields["radius"])
+        mylog.info("Integrating gravitational potential profile.")
+        tdens_func = InterpolatedUnivariateSpline(rr, fields["total_density"])
+        gpot_profile = lambda r: tdens_func(r) * r
+        gpot1 = fields["total_mass"] / fields["radius"]
+        gpot2 = 4.0 * np.pi * integrate(gpot_profile, rr)
+        fields["gravitational_potential"] = -G * (gpot1 + gpot2)
+
+        if "density" in fields and "gas_mass" not in fields:
+            mylog.info("Integrating gas mass profile.")
+            m0 = fields["density"][0] * rr[0] ** 3 / 3.0
+            fields["gas_mass"] = (
+                4.0 * np.pi * cumtrapz(fields["density"] * rr * rr, x=rr, initial=0.0) + m0
+            )
+
+        if stellar_density is not None:
+            fields["stellar_density"] = stellar_density(rr)
+            mylog.info("Integrating stellar mass profile.")
+            fields["stellar_mass"] = integrate_mass(stellar_density, rr)
+
+        mdm = np.array(fields["total_mass"], dtype=np.float64)
+        ddm = np.array(fields["total_density"], dtype=np.float64)
+        if "density" in fields:
+            mdm -= fields["gas_mass"]
+            ddm -= fields["density"]
+        if "stellar_mass" in fields:
+            mdm -= fields["stellar_mass"]
+            ddm -= fields["stellar_density"]
+        mdm[ddm < 0.0] = mdm.max()
+        ddm[ddm < 0.0] = 0.0
+        if ddm.sum() < 0.0 or mdm.sum() < 0.0:
+            mylog.warning("The total dark matter mass is either zero or negative!!")
+        fields["dark_matter_density"] = ddm
+        fields["dark_matter_mass"] = mdm
+
+        if "density" in fields:
+            fields["gas_fraction"] = fields["gas_mass"] / fields["total_mass"]
+        return cls(rr.size, fields)
+
+    @classmethod
+    def no_gas(cls, rmin, rmax, total_density, stellar_density=None, num_points=1000):
+        """Model without a gas component (model.py:620-656)."""
+        rr = np.logspace(np.log10(rmin), np.log10(rmax), num_points, endpoint=True)
+        fields = OrderedDict()
+        fields["radius"] = rr
+        fields["total_density"] = total_density(rr)
+        mylog.info("Integrating total mass profile.")
+        fields["total_mass"] = integrate_mass(total_density, rr)
+        fields["gravitational_field"] = -G * fields["total_mass"] / (fields["radius"] ** 2)
+        return cls._from_scratch(fields, stellar_density=stellar_density)
+
+    @classmethod
+    def from_dens_and_temp(cls, rmin, rmax, density, temperature, stellar_density=None, num_points=1000):
+        """Hydrostatic model from gas density and temperature (model.py:474-523)."""
+        mylog.info("Computing the profiles from density and temperature.")
+        rr = np.logspace(np.log10(rmin), np.log10(rmax), num_points, endpoint=True)
+        fields = OrderedDict()
+        fields["radius"] = rr
+        fields["density"] = density(rr)
+        fields["temperature"] = temperature(rr)
+        fields["pressure"] = fields["density"] * fields["temperature"]
+        fields["pressure"] = fields["pressure"] / (mu * mp)
+        fields["pressure"] = fields["pressure"] * keV
+        pressure_spline = InterpolatedUnivariateSpline(rr, fields["pressure"])
+        dPdr = pressure_spline(rr, 1)
+        fields["gravitational_field"] = dPdr / fields["density"]
+        fields["gas_mass"] = integrate_mass(density, rr)
+        fields["total_mass"] = -fields["radius"] ** 2 * fields["gravitational_field"] / G
+        total_mass_spline = InterpolatedUnivariateSpline(rr, fields["total_mass"])
+        dMdr = total_mass_spline(rr, nu=1)
+        fields["total_density"] = dMdr / (4.0 * np.pi * fields["radius"] ** 2)
+        return cls._from_scratch(fields, stellar_density=stellar_density)
+
+    @classmethod
+    def from_dens_and_tden(cls, rmin, rmax, density, total_density, stellar_density=None, num_points=1000):
+        """Hydrostatic model from gas density and total density (model.py:565-618)."""
+        mylog.info("Computing the profiles from density and total density.")
+        rr = np.logspace(np.log10(rmin), np.log10(rmax), num_points, endpoint=True)
+        fields = OrderedDict()
+        fields["radius"] = rr
+        fields["density"] = density(rr)
+        fields["total_density"] = total_density(rr)
+        fields["total_mass"] = integrate_mass(total_density, rr)
+        fields["gas_mass"] = integrate_mass(density, rr)
+        fields["gravitational_field"] = -G * fields["total_mass"] / (fields["radius"] ** 2)
+        g = fields["gravitational_field"]
+        g_r = InterpolatedUnivariateSpline(rr, g)
+        dPdr_int = lambda r: density(r) * g_r(r)
+        P = -integrate(dPdr_int, rr)
+        dPdr_int2 = lambda r: density(r) * g[-1] * (rr[-1] / r) ** 2
+        P -= quad(dPdr_int2, rr[-1], np.inf, limit=100)[0]
+        fields["pressure"] = P
+        fields["temperature"] = fields["pressure"] * mu * mp / fields["density"] / keV
+        return cls._from_scratch(fields, stellar_density=stellar_density)
+
+    # -- dict protocol (model.py:295-305) ------------------------------------
+    def __getitem__(self, key):
+        return self.fields[key]
+
+    def __contains__(self, key):
+        return key in self.fields
+
+    def keys(self):
+        return self.fields.keys()
+
+    def set_field(self, name, value):
+        """model.py:458-472"""
+        value = np.asarray(value)
+        if value.size != self.num_elements:
+            raise ValueError(f"The length of the array needs to be {self.num_elements} elements!")
+        if name in self.fields:
+            mylog.warning("Overwriting field %s." % name)
+        self.fields[name] = unit_array(value, _UNITS.get(name, ""))
+
+    def find_field_at_radius(self, field, r):
+        """model.py:658-665"""
+        return unit_array(np.interp(r, self["radius"].d, self[field].d), self[field].units)
+
+    # -- checks (model.py:667-716) -------------------------------------------
+    def check_hse(self):
+        if "pressure" not in self.fields:
+            raise RuntimeError("This ClusterModel contains no gas!")
+        rr = self.fields["radius"].d
+        pressure_spline = InterpolatedUnivariateSpline(rr, self.fields["pressure"].d)
+        dPdx = pressure_spline(rr, 1)
+        rhog = self.fields["density"].d * self.fields["gravitational_field"].d
+        chk = (dPdx - rhog) / rhog
+        mylog.info("The maximum relative deviation of this profile from hydrostatic equilibrium is %g",
+                   np.abs(chk).max())
+        return chk
+
+    def check_dm_virial(self):
+        return self.dm_virial.check_virial()
+
+    def check_star_virial(self):
+        return self.star_virial.check_virial()
+
+    # -- particle generation ---------------------------------------------------
+    def generate_dm_particles(self, num_particles, r_max=None, sub_sample=1, compute_potential=False,
+                              prng=None, **kw) -> ClusterParticles:
+        """Dark matter particles in virial equilibrium (model.py:949-993)."""
+        return self.dm_virial.generate_particles(
+            num_particles, r_max=r_max, sub_sample=sub_sample, compute_potential=compute_potential,
+            prng=prng, **kw)
+
+    def generate_star_particles(self, num_particles, r_max=None, sub_sample=1, compute_potential=False,
+                                prng=None, **kw) -> ClusterParticles:
+        """Star particles in virial equilibrium (model.py:995-1039)."""
+        return self.star_virial.generate_particles(
+            num_particles, r_max=r_max, sub_sample=sub_sample, compute_potential=compute_potential,
+            prng=prng, **kw)
+
+    def _gas_sampler_tables(self, r_max, tracer) -> SamplerTables:
+        key = (None if r_max is None else float(r_max), bool(tracer))
+        if key not in self._gas_tables:
+            rr = self["radius"].d
+            # gas / tracer radii use ALL rows (model.py:803-809, 879-885): no rho > 0 mask
+            P_r, r_cdf, mtot = radius_cdf_table(rr, self["gas_mass"].d, r_max)
+            psi_spline = DeviceSpline.fit(rr, -self["gravitational_potential"].d)  # model.py:939-941
+            aux = []
+            if not tracer:
+                e_arr = 1.5 * self["pressure"].d / self["density"].d                # model.py:908
+                aux = [DeviceSpline.fit(rr, e_arr), DeviceSpline.fit(rr, self["density"].d)]
+            self._gas_tables[key] = SamplerTables(P_r, r_cdf, mtot, psi_spline, None, aux)
+        return self._gas_tables[key]
+
+    def _generate_radial(self, ptype, num_particles, r_max, sub_sample, compute_potential, prng,
+                         dtype, rng, shard):
+        if "gas_mass" not in self.fields:
+            raise RuntimeError("This ClusterModel contains no gas!")
+        num_particles, sub_sample = int(num_particles), int(sub_sample)
+        if sub_sample < 1 or num_particles % sub_sample != 0:
+            raise ValueError("num_particles must be a multiple of sub_sample")
+        if sub_sample != 1:
+            raise NotImplementedError("sub_sample > 1 is only supported for dm/star particles")
+        if rng not in ("device", "numpy"):
+            raise ValueError("rng must be 'device' or 'numpy'")
+        tracer = ptype == "tracer"
+        prng = parse_prng(prng)
+        dev = N.require_cuda()
+        tabs = self._gas_sampler_tables(r_max, tracer)
+        lo, hi = shard_bounds(num_particles, shard)
+        n_loc = hi - lo
+        code = _out_code(dtype)
+        keep = []
+        a = N.SampleArgs()
+        if rng == "numpy":
+            u_r = prng.uniform(size=num_particles)   # model.py:879-885 -> utils.py:161
+            u_ct = prng.uniform(size=num_particles)  # model.py:892
+            u_ph = prng.uniform(size=num_particles)  # model.py:893
+            for name, arr in (("d_u_r", u_r), ("d_u_ct", u_ct), ("d_u_ph", u_ph)):
+                t = N.dev_f64(arr[lo:hi], dev)
+                keep.append(t)
+                setattr(a.hu, name, t.data_ptr())
+            seed = PRIVATE_TRIAL_SEED
+        else:
+            seed = seed_from_prng(prng, 4 if tracer else 3)
+        pos = torch.empty((3, n_loc), dtype=dtype, device=dev)
+        vel = torch.empty((3, n_loc), dtype=dtype, device=dev)
+        mass = torch.empty(n_loc, dtype=dtype, device=dev)
+        pot = torch.empty(n_loc, dtype=dtype, device=dev) if compute_potential else None
+        therm = dens = None
+        if not tracer:
+            therm = torch.empty(n_loc, dtype=dtype, device=dev)
+            dens = torch.empty(n_loc, dtype=dtype, device=dev)
+        a.d_workspace = tabs.workspace.data_ptr()
+        a.id_begin, a.id_end, a.ld = lo, hi, n_loc
+        # tracers carry zero mass (model.py:834); gas mtot / n (model.py:917-919)
+        a.particle_mass = 0.0 if tracer else (tabs.mtot / num_particles if num_particles else 0.0)
+        a.seed = seed & 0xFFFFFFFFFFFFFFFF
+        a.out_dtype = code
+        a.d_pos, a.d_vel, a.d_mass = pos.data_ptr(), vel.data_ptr(), mass.data_ptr()
+        a.d_pot = pot.data_ptr() if pot is not None else None
+        if n_loc > 0:
+            N.check(N.lib().cgb_sample_gas(N.ctypes.byref(a), N.ptr(therm), N.ptr(dens), N.stream_ptr()))
+        fields = OrderedDict()
+        fields[ptype, "particle_position"] = pos.T
+        if not tracer:
+            fields[ptype, "thermal_energy"] = therm
+        fields[ptype, "particle_mass"] = mass
+        if not tracer:
+            fields[ptype, "density"] = dens
+        fields[ptype, "particle_velocity"] = vel.T
+        if compute_potential:
+            fields[ptype, "particle_potential"] = pot
+        del keep
+        return ClusterParticles(ptype, fields)
+
+    def generate_gas_particles(self, num_particles, r_max=None, sub_sample=1, compute_potential=False,
+                               prng=None, *, dtype=torch.float64, rng="device", shard=None):
+        """Gas particles in hydrostatic equilibrium (model.py:838-947)."""
+        return self._generate_radial("gas", num_particles, r_max, sub_sample, compute_potential, prng,
+                                     dtype, rng, shard)
+
+    def generate_tracer_particles(self, num_particles, r_max=None, sub_sample=1, prng=None, *,
+                                  dtype=torch.float64, rng="device", shard=None):
+        """Tracer particles following the gas distribution (model.py:766-836)."""
+        return self._generate_radial("tracer", num_particles, r_max, sub_sample, False, prng, dtype,
+                                     rng, shard)

@@ -1,0 +1,112 @@
+"""
+Host-side utilities of the particle path: constants, the ``quad``-based table
+integrators, prng parsing and the tiny unit-tagged ndarray used for model fields.
+
+Mirrors ``cluster_generator/utils.py`` (reference) for the names the hot path uses:
+``G, mp, mu, mue`` (utils.py:116-123), ``integrate_mass`` (:129-134), ``integrate``
+(:137-142), ``parse_prng`` (:184-188), ``mylog`` (:66-78).
+"""
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+from numpy.random import RandomState
+from scipy.integrate import quad
+
+mylog = logging.getLogger("cluster_generator_b200")
+if not mylog.handlers:
+    _h = logging.StreamHandler()
+    _h.setFormatter(logging.Formatter("%(name)-3s : [%(levelname)-9s] %(asctime)s %(message)s"))
+    mylog.addHandler(_h)
+    mylog.setLevel(logging.WARNING)
+    mylog.propagate = False
+
+# unyt is not a dependency here; these are the values unyt's CODATA-2014 tables give
+# for the conversions at utils.py:116-119 (recorded in DESIGN.md).
+_G_MKS = 6.67408e-11
+_MSUN_KG = 1.98841586e30
+_SEC_PER_MYR = 31557600.0 * 1.0e6
+_M_PER_KPC = 3.0856775809623245e19
+_MP_KG = 1.672621898e-27
+_J_PER_KEV = 1.6021766208e-16
+
+G = _G_MKS * _MSUN_KG * _SEC_PER_MYR**2 / _M_PER_KPC**3  #: kpc**3/Msun/Myr**2
+mp = _MP_KG / _MSUN_KG  #: Msun
+keV = _J_PER_KEV / _MSUN_KG * _SEC_PER_MYR**2 / _M_PER_KPC**2  #: Msun*kpc**2/Myr**2
+kpc_to_cm = _M_PER_KPC * 100.0
+
+X_H = 0.76  # bin/config.yaml: physics.hydrogen_abundance
+mu = 1.0 / (2.0 * X_H + 0.75 * (1.0 - X_H))
+mue = 1.0 / (X_H + 0.5 * (1.0 - X_H))
+
+
+class unit_array(np.ndarray):
+    """ndarray with a ``units`` string and unyt's ``.d`` / ``.v`` accessors."""
+
+    def __new__(cls, value, units=""):
+        obj = np.asarray(value, dtype=np.float64).view(cls)
+        obj.units = units
+        return obj
+
+    def __array_finalize__(self, obj):
+        self.units = getattr(obj, "units", "")
+
+    @property
+    def d(self):
+        return np.asarray(self)
+
+    v = d
+    value = d
+
+
+def integrate_mass(profile, rr):
+    """M(<r) = 4 pi int_0^r rho r^2 dr, one ``quad`` per radius (utils.py:129-134)."""
+    mass_int = lambda r: profile(r) * r * r
+    mass = np.zeros(rr.shape)
+    for i, r in enumerate(rr):
+        mass[i] = 4.0 * np.pi * quad(mass_int, 0, r)[0]
+    return mass
+
+
+def integrate(profile, rr):
+    """int_r^rmax profile dr, one ``quad`` per radius (utils.py:137-142)."""
+    ret = np.zeros(rr.shape)
+    rmax = rr[-1]
+    for i, r in enumerate(rr):
+        ret[i] = quad(profile, r, rmax)[0]
+    return ret
+
+
+def integrate_toinf(profile, rr):
+    """utils.py:145-151"""
+    ret = np.zeros(rr.shape)
+    rmax = rr[-1]
+    for i, r in enumerate(rr):
+        ret[i] = quad(profile, r, rmax)[0]
+    ret[:] += quad(profile, rmax, np.inf, limit=100)[0]
+    return ret
+
+
+def parse_prng(prng):
+    """utils.py:184-188"""
+    if isinstance(prng, RandomState):
+        return prng
+    return RandomState(prng)
+
+
+def seed_from_prng(prng: RandomState, species: int) -> int:
+    """64-bit Philox key for one generation call.
+
+    Drawn from the caller's MT19937 stream, so a fixed ``prng`` reproduces the whole
+    sequence of calls (like the reference's shared ``RandomState``) while successive
+    calls and different species get independent Philox streams.
+    """
+    lo, hi = (int(x) for x in prng.randint(0, 2**32, size=2, dtype=np.uint64))
+    return (lo | (hi << 32)) ^ ((species * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF)
+
+
+def ensure_list(x):
+    if isinstance(x, (list, tuple, set)):
+        return list(x)
+    return [x]

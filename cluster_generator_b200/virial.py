@@ -1,0 +1,417 @@
+"""
+Equilibrium sampler: Eddington f(E), virial check, DM/star particle generation.
+
+Drop-in mirror of ``cluster_generator.virial.VirialEquilibrium`` (virial.py:16-236):
+same constructor, ``f / df / ee / ff``, ``check_virial()`` and
+``generate_particles()`` with the reference's argument meaning and error behaviour.
+All numerics run in hand-written sm_100a CUDA behind the C ABI of
+``include/cgb200.h``; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _native as N
+from .particles import ClusterParticles
+from .utils import mylog, parse_prng, seed_from_prng, unit_array
+
+#: Philox key used for the speed trials when the caller asks for numpy-ordered
+#: uniforms (rng="numpy"): like the reference's Cython loop, the trial stream is then
+#: private and does not consume the caller's ``prng``.
+PRIVATE_TRIAL_SEED = 0xC6A4A7935BD1E995
+
+_SPECIES = {"dark_matter": 1, "stellar": 2, "gas": 3, "tracer": 4}
+
+
+class DeviceSpline:
+    """Cubic interpolating spline living on the GPU.
+
+    Stands in for ``scipy.interpolate.InterpolatedUnivariateSpline`` where the
+    reference keeps one as ``VirialEquilibrium.f`` (virial.py:41,67): callable with
+    ``(x, nu=0|1)``, ``get_knots()``, ``get_coeffs()`` and ``_eval_args``.
+    """
+
+    def __init__(self, t: torch.Tensor, c: torch.Tensor):
+        self.t, self.c = t, c
+        self.n = c.numel()
+
+    @classmethod
+    def fit(cls, x, y) -> "DeviceSpline":
+        """IUS(x, y): raises ValueError unless x is strictly increasing (as scipy does)."""
+        xh = np.asarray(x, dtype=np.float64)
+        yh = np.asarray(y, dtype=np.float64)
+        if xh.ndim != 1 or xh.shape != yh.shape:
+            raise ValueError("x and y should be 1-d arrays of the same length")
+        if xh.size < 4:
+            raise ValueError("need at least 4 points for a cubic spline")
+        if not np.all(np.diff(xh) > 0.0):
+            raise ValueError("x must be strictly increasing")
+        if not (np.all(np.isfinite(xh)) and np.all(np.isfinite(yh))):
+            raise ValueError("x and y must be finite")
+        dev = N.require_cuda()
+        n = xh.size
+        xd, yd = N.dev_f64(xh, dev), N.dev_f64(yh, dev)
+        t = torch.empty(n + 4, dtype=torch.float64, device=dev)
+        c = torch.empty(n, dtype=torch.float64, device=dev)
+        nb = N.lib().cgb_spline_fit_workspace_bytes(n)
+        work = N.workspace(nb, dev)
+        N.check(N.lib().cgb_spline_fit(N.ptr(xd), N.ptr(yd), n, N.ptr(t), N.ptr(c), N.ptr(work), nb,
+                                       N.stream_ptr()))
+        return cls(t, c)
+
+    def __call__(self, x, nu=0):
+        dev = self.t.device
+        xh = np.atleast_1d(np.asarray(x, dtype=np.float64))
+        xd = N.dev_f64(xh.ravel(), dev)
+        yd = torch.empty_like(xd)
+        N.check(N.lib().cgb_spline_eval(N.ptr(self.t), N.ptr(self.c), self.n, N.ptr(xd), N.ptr(yd),
+                                        xd.numel(), int(nu), N.stream_ptr()))
+        y = yd.cpu().numpy().reshape(xh.shape)
+        return y if np.ndim(x) else float(y[0])
+
+    def get_knots(self):
+        return self.t[3:-3].cpu().numpy()
+
+    def get_coeffs(self):
+        return self.c.cpu().numpy()
+
+    @property
+    def _eval_args(self):
+        return self.t.cpu().numpy(), self.c.cpu().numpy(), 3
+
+
+class SamplerTables:
+    """Device tables of one (species, r_max): CDF, psi(r), f(E), screen; see
+    ``cgb_sampler_prepare``."""
+
+    def __init__(self, P_r, r_cdf, mtot, psi_spline: DeviceSpline, f_spline: DeviceSpline | None,
+                 aux: list[DeviceSpline] | None = None):
+        dev = N.require_cuda()
+        self.mtot = float(mtot)
+        self.P_r, self.r_cdf = N.dev_f64(P_r, dev), N.dev_f64(r_cdf, dev)
+        self.psi_spline, self.f_spline, self.aux = psi_spline, f_spline, aux or []
+        d = N.SamplerDesc()
+        d.d_cdf_P, d.d_cdf_r, d.n_cdf = self.P_r.data_ptr(), self.r_cdf.data_ptr(), self.P_r.numel()
+        d.n_psi, d.d_psi_t, d.d_psi_c = psi_spline.n, psi_spline.t.data_ptr(), psi_spline.c.data_ptr()
+        if f_spline is not None:
+            d.n_f, d.d_f_t, d.d_f_c = f_spline.n, f_spline.t.data_ptr(), f_spline.c.data_ptr()
+        d.n_aux = len(self.aux)
+        for k, s in enumerate(self.aux):
+            d.n_aux_coef = s.n
+            d.d_aux_t[k], d.d_aux_c[k] = s.t.data_ptr(), s.c.data_ptr()
+        nb = N.lib().cgb_sampler_workspace_bytes(N.ctypes.byref(d))
+        if nb == 0:
+            N.check(N.CGB_E_INVALID)
+        self.workspace = N.workspace(nb, dev)
+        N.check(N.lib().cgb_sampler_prepare(N.ctypes.byref(d), N.ptr(self.workspace), nb, N.stream_ptr()))
+        self.tile_counter = torch.zeros(1, dtype=torch.int64, device=dev)
+
+
+def radius_cdf_table(r, m, r_max=None):
+    """The (P_r, r) table of generate_particle_radii (utils.py:155-164), built on the
+    host from the N-point model arrays (the per-particle draw happens on the GPU)."""
+    ridx = r.size if r_max is None else int(np.searchsorted(r, r_max))
+    if ridx < 1:
+        raise ValueError(f"r_max = {r_max} lies inside the innermost radius {r[0]}")
+    mtot = m[ridx - 1]
+    P_r = np.insert(m[:ridx], 0, 0.0)
+    P_r /= P_r[-1]
+    rr = np.insert(r[:ridx], 0, 0.0)
+    return P_r, rr, float(mtot)
+
+
+def shard_bounds(n: int, shard):
+    """Contiguous index range of rank k of G: [k n / G, (k+1) n / G)."""
+    if shard is None:
+        return 0, n
+    rank, world = shard
+    if not (0 <= rank < world):
+        raise ValueError(f"bad shard {shard}")
+    return (rank * n) // world, ((rank + 1) * n) // world
+
+
+def _out_code(dtype):
+    if dtype == torch.float64:
+        return N.CGB_DTYPE_F64
+    if dtype == torch.float32:
+        return N.CGB_DTYPE_F32
+    raise ValueError(f"dtype must be torch.float64 or torch.float32, got {dtype}")
+
+
+class VirialEquilibrium:
+    def __init__(self, model, ptype="dark_matter", df=None):
+        r"""
+        Generate a virial equilibrium model from a profile (virial.py:17-41).
+
+        Parameters
+        ----------
+        model : ClusterModel
+        ptype : "dark_matter" or "stellar"
+        df : array, optional
+            The particle distribution function in radius order. If not supplied, it
+            is generated on the GPU.
+        """
+        if ptype not in ("dark_matter", "stellar"):
+            raise KeyError(ptype)
+        self.num_elements = model.num_elements
+        self.ptype = ptype
+        self.model = model
+        self._tables = {}
+        self.g = None
+        self.qags_last = self.qags_ier = None
+        if df is None:
+            self._generate_df()
+        else:
+            self.df = unit_array(np.asarray(df, dtype=np.float64), "Msun*Myr**3/kpc**6")
+            self.f = DeviceSpline.fit(self.ee, self.df.d[::-1])
+
+    def _generate_df(self):
+        """Eddington inversion on the device (virial.py:43-68)."""
+        n = self.num_elements
+        ee = np.ascontiguousarray(self.ee)
+        pden = np.ascontiguousarray(self.model[f"{self.ptype}_density"].d[::-1])
+        if not np.all(np.diff(ee) > 0.0):
+            raise ValueError("x must be strictly increasing")
+        dev = N.require_cuda()
+        L = N.lib()
+        ee_d, pd_d = N.dev_f64(ee, dev), N.dev_f64(pden, dev)
+        g = torch.empty(n, dtype=torch.float64, device=dev)
+        ff = torch.empty(n, dtype=torch.float64, device=dev)
+        ft = torch.empty(n + 4, dtype=torch.float64, device=dev)
+        fc = torch.empty(n, dtype=torch.float64, device=dev)
+        last = torch.empty(n, dtype=torch.int32, device=dev)
+        ier = torch.empty(n, dtype=torch.int32, device=dev)
+        nb = L.cgb_eddington_workspace_bytes(n)
+        work = N.workspace(nb, dev)
+        N.check(L.cgb_eddington_df(N.ptr(ee_d), N.ptr(pd_d), n, 1.49e-05, 1.49e-05, N.ptr(g), N.ptr(ff),
+                                   N.ptr(ft), N.ptr(fc), N.ptr(last), N.ptr(ier), N.ptr(work), nb,
+                                   N.stream_ptr()))
+        self.f = DeviceSpline(ft, fc)
+        self.g = g.cpu().numpy()
+        self.qags_last, self.qags_ier = last.cpu().numpy(), ier.cpu().numpy()
+        self.df = unit_array(ff.cpu().numpy()[::-1].copy(), "Msun*Myr**3/kpc**6")
+
+    @property
+    def ee(self):
+        """Relative potential in ascending order (virial.py:70-72)."""
+        return -self.model["gravitational_potential"].d[::-1]
+
+    @property
+    def ff(self):
+        """f(E) in ascending-E order (virial.py:74-76)."""
+        return self.df.d[::-1]
+
+    def check_virial(self):
+        r"""
+        Density profile implied by f(E) and its relative deviation from the input
+        profile (virial.py:78-106).  Returns ``(rho, chk)`` in radius order.
+        """
+        n = self.num_elements
+        dev = N.require_cuda()
+        ee_d = N.dev_f64(np.ascontiguousarray(self.ee), dev)
+        pd_d = N.dev_f64(np.ascontiguousarray(self.model[f"{self.ptype}_density"].d[::-1]), dev)
+        rho = torch.empty(n, dtype=torch.float64, device=dev)
+        chk = torch.empty(n, dtype=torch.float64, device=dev)
+        N.check(N.lib().cgb_check_virial(N.ptr(ee_d), N.ptr(pd_d), n, N.ptr(self.f.t), N.ptr(self.f.c),
+                                         N.ptr(rho), N.ptr(chk), None, None, N.stream_ptr()))
+        rho, chk = rho.cpu().numpy(), chk.cpu().numpy()
+        mylog.info(
+            "The maximum relative deviation of this profile from virial equilibrium is %g",
+            np.abs(chk).max(),
+        )
+        return rho, chk
+
+    # ------------------------------------------------------------------ #
+    def sampler_tables(self, r_max=None) -> SamplerTables:
+        """Device tables for this species and r_max (cached)."""
+        key = None if r_max is None else float(r_max)
+        if key not in self._tables:
+            density = f"{self.ptype}_density"
+            mass = f"{self.ptype}_mass"
+            nonzero = self.model[density].d > 0.0  # virial.py:161
+            P_r, r_cdf, mtot = radius_cdf_table(
+                self.model["radius"].d[nonzero], self.model[mass].d[nonzero], r_max
+            )
+            # energy_spline = IUS(radius, psi)                        (virial.py:152-154)
+            psi_spline = DeviceSpline.fit(self.model["radius"].d, self.ee[::-1])
+            self._tables[key] = SamplerTables(P_r, r_cdf, mtot, psi_spline, self.f)
+        return self._tables[key]
+
+    def generate_particles(
+        self,
+        num_particles,
+        r_max=None,
+        sub_sample=1,
+        compute_potential=False,
+        prng=None,
+        *,
+        dtype=torch.float64,
+        rng="device",
+        shard=None,
+        diagnostics=True,
+    ):
+        """
+        Generate a set of dark matter or star particles in virial equilibrium
+        (virial.py:108-236).
+
+        Parameters (reference signature)
+        --------------------------------
+        num_particles, r_max, sub_sample, compute_potential, prng : as the reference.
+
+        Extensions (keyword-only)
+        -------------------------
+        dtype : torch.float64 (default) or torch.float32 output buffers.
+        rng : "device" (default) -- every uniform comes from Philox4x32-10 keyed by a
+            seed drawn from ``prng``; "numpy" -- radii and directions use uniforms
+            drawn from ``prng`` in the reference's order (virial.py:162,175-176,
+            213-214), so those fields equal the reference's for the same ``prng``.
+        shard : (rank, world) -- generate only this rank's contiguous index range;
+            output is bit-identical to the corresponding slice of a single-GPU run.
+        """
+        num_particles = int(num_particles)
+        sub_sample = int(sub_sample)
+        if num_particles < 0:
+            raise ValueError("num_particles must be non-negative")
+        if sub_sample < 1:
+            raise ValueError("sub_sample must be >= 1")
+        if num_particles % sub_sample != 0:
+            # the reference fails later with a broadcasting ValueError (virial.py:182)
+            raise ValueError("num_particles must be a multiple of sub_sample")
+        if rng not in ("device", "numpy"):
+            raise ValueError("rng must be 'device' or 'numpy'")
+        num_particles_sub = num_particles // sub_sample
+        key = {"dark_matter": "dm", "stellar": "star"}[self.ptype]
+        prng = parse_prng(prng)
+        mylog.info("We will be assigning %s %s particles.", num_particles, self.ptype)
+
+        dev = N.require_cuda()
+        L = N.lib()
+        tabs = self.sampler_tables(r_max)
+        code = _out_code(dtype)
+        lo, hi = shard_bounds(num_particles, shard)
+        n_loc = hi - lo
+
+        hu = {}
+        if rng == "numpy":
+            # reference draw order: u_r[n_sub], cos(theta)[n], phi[n], (speeds), cos, phi
+            hu["u_r"] = prng.uniform(size=num_particles_sub)
+            hu["u_ct"] = prng.uniform(size=num_particles)
+            hu["u_ph"] = prng.uniform(size=num_particles)
+            hu["u_ctv"] = prng.uniform(size=num_particles)
+            hu["u_phv"] = prng.uniform(size=num_particles)
+            seed = PRIVATE_TRIAL_SEED
+        else:
+            seed = seed_from_prng(prng, _SPECIES[self.ptype])
+
+        pos = torch.empty((3, n_loc), dtype=dtype, device=dev)
+        vel = torch.empty((3, n_loc), dtype=dtype, device=dev)
+        mass = torch.empty(n_loc, dtype=dtype, device=dev)
+        pot = torch.empty(n_loc, dtype=dtype, device=dev) if compute_potential else None
+        moments = torch.zeros(N.CGB_NMOMENTS, dtype=torch.float64, device=dev) if diagnostics else None
+        pmass = tabs.mtot / num_particles if num_particles > 0 else 0.0  # virial.py:225-227
+
+        def base_args(begin, end, ld):
+            a = N.SampleArgs()
+            a.d_workspace = tabs.workspace.data_ptr()
+            a.id_begin, a.id_end = begin, end
+            a.particle_mass = pmass
+            a.seed = seed & 0xFFFFFFFFFFFFFFFF
+            a.out_dtype = code
+            a.ld = ld
+            return a
+
+        keep = []  # keep device uniforms alive until the kernels are enqueued
+
+        def host_u(a, begin, end, sub):
+            if not hu:
+                return
+            def put(name, b, e):
+                t = N.dev_f64(hu[name][b:e], dev)
+                keep.append(t)
+                return t.data_ptr()
+            if sub:
+                a.hu.d_u_r = put("u_r", begin, end)
+            a.hu.d_u_ct, a.hu.d_u_ph = put("u_ct", begin, end), put("u_ph", begin, end)
+            a.hu.d_u_ctv, a.hu.d_u_phv = put("u_ctv", begin, end), put("u_phv", begin, end)
+
+        if n_loc > 0 and sub_sample == 1:
+            a = base_args(lo, hi, n_loc)
+            a.d_pos, a.d_vel, a.d_mass = pos.data_ptr(), vel.data_ptr(), mass.data_ptr()
+            a.d_pot = pot.data_ptr() if pot is not None else None
+            a.d_moments = moments.data_ptr() if moments is not None else None
+            host_u(a, lo, hi, True)
+            tabs.tile_counter.zero_()
+            N.check(L.cgb_sample_particles(N.ctypes.byref(a), N.ptr(tabs.tile_counter), N.stream_ptr()))
+        elif n_loc > 0:
+            # unique (r, |v|) for n_sub particles, tiled over all n (virial.py:170-173,208-211)
+            ns = num_particles_sub
+            r_sub = torch.empty(ns, dtype=torch.float64, device=dev)
+            v_sub = torch.empty(ns, dtype=torch.float64, device=dev)
+            psi_sub = torch.empty(ns, dtype=torch.float64, device=dev)
+            scratch = torch.empty((2, 3, ns), dtype=dtype, device=dev)
+            a = base_args(0, ns, ns)
+            a.d_pos, a.d_vel = scratch[0].data_ptr(), scratch[1].data_ptr()
+            a.d_radius, a.d_speed = r_sub.data_ptr(), v_sub.data_ptr()
+            a.d_pot = None
+            a.d_moments = moments.data_ptr() if moments is not None else None
+            if hu:
+                t = N.dev_f64(hu["u_r"], dev)
+                keep.append(t)
+                a.hu.d_u_r = t.data_ptr()
+            tabs.tile_counter.zero_()
+            N.check(L.cgb_sample_particles(N.ctypes.byref(a), N.ptr(tabs.tile_counter), N.stream_ptr()))
+            if compute_potential:
+                N.check(L.cgb_spline_eval(N.ptr(tabs.psi_spline.t), N.ptr(tabs.psi_spline.c),
+                                          tabs.psi_spline.n, N.ptr(r_sub), N.ptr(psi_sub), ns, 0,
+                                          N.stream_ptr()))
+            b = base_args(lo, hi, n_loc)
+            b.d_pos, b.d_vel, b.d_mass = pos.data_ptr(), vel.data_ptr(), mass.data_ptr()
+            b.d_pot = pot.data_ptr() if pot is not None else None
+            host_u(b, lo, hi, False)
+            N.check(L.cgb_assemble_particles(N.ctypes.byref(b), N.ptr(r_sub), N.ptr(v_sub),
+                                             N.ptr(psi_sub) if compute_potential else None, ns,
+                                             N.stream_ptr()))
+
+        fields = OrderedDict()
+        fields[key, "particle_position"] = pos.T
+        fields[key, "particle_velocity"] = vel.T
+        fields[key, "particle_mass"] = mass
+        if compute_potential:
+            fields[key, "particle_potential"] = pot
+        diag = {}
+        if moments is not None:
+            diag[key] = SamplerDiagnostics(moments, shard)
+        del keep
+        return ClusterParticles(key, fields, diag)
+
+
+class SamplerDiagnostics:
+    """Kernel-side moments of one generation call (lazy D2H; optional all-reduce)."""
+
+    def __init__(self, moments: torch.Tensor, shard=None):
+        self.moments = moments
+        self.shard = shard
+
+    def all_reduce(self):
+        """Sum the moments over the ranks of the default process group (NCCL on GPUs);
+        the only collective of the path."""
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            mx = self.moments[2:3].clone()
+            dist.all_reduce(self.moments, op=dist.ReduceOp.SUM)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            self.moments[2:3] = mx
+        return self
+
+    def as_dict(self):
+        m = self.moments.cpu().numpy()
+        d = dict(zip(N.MOMENT_NAMES, (float(x) for x in m)))
+        n = max(d["particles"] - d["failures"], 1.0)
+        d["mean_trials"] = d["sum_trials"] / n
+        d["mean_v2"] = d["sum_v2"] / n
+        d["mean_psi"] = d["sum_psi"] / n
+        return d

@@ -1,0 +1,226 @@
+/*
+ * cgb200.h -- C ABI of libcgb200.so: the B200 (sm_100a) particle-sampling engine
+ * that stands in for the native/numeric part of cluster_generator's particle path.
+ *
+ * Every entry point cites the reference interface it replaces (file:line into
+ * /root/reference/cluster_generator).  Conventions:
+ *
+ *   - all functions return int: 0 = ok, <0 = CGB_E_*; the message for the last
+ *     failure on the calling thread is cgb_last_error().  Nothing throws or aborts
+ *     across this boundary.
+ *   - every pointer named d_* (and every pointer inside the structs) is a DEVICE
+ *     pointer owned by the caller (PyTorch: tensor.data_ptr()); the library never
+ *     allocates, frees or retains caller memory.  Scratch is caller-provided
+ *     ("workspace"), sized by the *_workspace_bytes functions.
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *     calls are asynchronous on that stream unless stated otherwise.
+ *   - one host thread per GPU; the library holds no global mutable state except
+ *     the thread-local error string.
+ *
+ * Random-number contract (shared with oracle/cg_oracle_c.c, "mode B"):
+ *   Philox4x32-10, key = (seed_lo, seed_hi), counter = (id_lo, id_hi, c2, stream)
+ *   with id the GLOBAL particle index, so output is a pure function of
+ *   (tables, seed, id) and identical for any sharding over GPUs.
+ *     stream CGB_STREAM_RADIUS   c2=0: u_r   = u52(w0,w1)
+ *     stream CGB_STREAM_POS_DIR  c2=0: u_cos = u52(w0,w1), u_phi = u52(w2,w3)
+ *     stream CGB_STREAM_VEL_TRIAL c2=p: trial 2p   uses u1 = w0*2^-32, u2 = w1*2^-32
+ *                                       trial 2p+1 uses u1 = w2*2^-32, u2 = w3*2^-32
+ *     stream CGB_STREAM_VEL_DIR  c2=0: u_cos = u52(w0,w1), u_phi = u52(w2,w3)
+ *   u52(hi,lo) = bits_to_double(0x3FF0000000000000 | hi<<20 | lo>>12) - 1.0
+ */
+#ifndef CGB200_H
+#define CGB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CGB_VERSION 100
+
+#define CGB_OK 0
+#define CGB_E_INVALID (-1)   /* bad argument (ValueError on the Python side)          */
+#define CGB_E_CUDA (-2)      /* CUDA runtime error (RuntimeError)                      */
+#define CGB_E_WORKSPACE (-3) /* workspace too small / misaligned                       */
+#define CGB_E_NOTMONO (-4)   /* abscissa not strictly increasing ("x must be increasing",
+                                what InterpolatedUnivariateSpline raises at virial.py:45) */
+
+#define CGB_STREAM_RADIUS 0u
+#define CGB_STREAM_POS_DIR 1u
+#define CGB_STREAM_VEL_TRIAL 2u
+#define CGB_STREAM_VEL_DIR 3u
+
+#define CGB_DTYPE_F64 0
+#define CGB_DTYPE_F32 1
+
+int cgb_version(void);
+const char *cgb_last_error(void);
+
+/* Number of SMs / FP64 FMA microbenchmark used for the roofline denominator
+ * (bench.py).  cgb_measure_dfma_tflops launches a register-resident DFMA loop and
+ * returns achieved TFLOP/s (2 flop per FMA) through *tflops (host pointer; syncs). */
+int cgb_device_sm_count(int *sm_count);
+int cgb_measure_dfma_tflops(int iters, double *tflops, void *stream);
+int cgb_measure_ffma_tflops(int iters, double *tflops, void *stream);
+
+/* ------------------------------------------------------------------------ */
+/* Cubic interpolating splines, FITPACK-compatible                           */
+/*   replaces scipy.interpolate.InterpolatedUnivariateSpline(x, y) (k=3,     */
+/*   s=0, ext=0) as used at virial.py:41,45,65,67,152 and model.py:909,921,939 */
+/* ------------------------------------------------------------------------ */
+/* Fit: knots t = [x0]*4 + x[2:-2] + [x_{n-1}]*4 (n+4 values), n coefficients.
+ * d_work: >= cgb_spline_fit_workspace_bytes(n) bytes.  Returns CGB_E_NOTMONO through
+ * *d_status (device int, nullable) -- asynchronous, so monotonicity is reported on
+ * the device; the Python wrapper checks it on the host before calling. */
+size_t cgb_spline_fit_workspace_bytes(int n);
+int cgb_spline_fit(const double *d_x, const double *d_y, int n, double *d_t, double *d_c,
+                   void *d_work, size_t work_bytes, void *stream);
+/* Evaluate the spline (nu = 0) or its first derivative (nu = 1) at m points
+ * (FITPACK splev/splder arithmetic, extrapolating outside the knots). */
+int cgb_spline_eval(const double *d_t, const double *d_c, int n, const double *d_x, double *d_y,
+                    int64_t m, int nu, void *stream);
+
+/* ------------------------------------------------------------------------ */
+/* D: Eddington distribution function                                        */
+/*   replaces VirialEquilibrium._generate_df  (virial.py:43-68)              */
+/* ------------------------------------------------------------------------ */
+/* in : d_ee[n] ascending relative potential, d_pden[n] density in the same order.
+ * out: d_g[n] (the QAGS integrals, virial.py:54-63), d_ff[n] = g'(E)/(sqrt(8) pi^2)
+ *      (virial.py:65-66), and the spline of ff: d_f_t[n+4], d_f_c[n] (virial.py:67).
+ *      d_last[n], d_ier[n] (nullable): QAGS sub-interval count / error flag per bin.
+ * The quadrature is a decision-for-decision restatement of QUADPACK dqagse
+ * (21-point Gauss-Kronrod, bisection, epsilon extrapolation, limit = 50). */
+size_t cgb_eddington_workspace_bytes(int n);
+int cgb_eddington_df(const double *d_ee, const double *d_pden, int n, double epsabs, double epsrel,
+                     double *d_g, double *d_ff, double *d_f_t, double *d_f_c, int *d_last,
+                     int *d_ier, void *d_work, size_t work_bytes, void *stream);
+
+/* ------------------------------------------------------------------------ */
+/* C: virial self-check                                                      */
+/*   replaces VirialEquilibrium.check_virial  (virial.py:78-106)             */
+/* ------------------------------------------------------------------------ */
+/* rho_chk(psi_i) = 4 pi int_0^{psi_i} f(E) sqrt(2 (psi_i - E)) dE, QAGS with the
+ * scipy defaults epsabs = epsrel = 1.49e-8, limit = 50.
+ * d_rho[n], d_chk[n] come back in RADIUS order like the reference (rho[::-1]);
+ * d_pden[n] is in ascending-psi order (the caller's reversed density). */
+int cgb_check_virial(const double *d_ee, const double *d_pden, int n, const double *d_f_t,
+                     const double *d_f_c, double *d_rho, double *d_chk, int *d_last, int *d_ier,
+                     void *stream);
+
+/* ------------------------------------------------------------------------ */
+/* Sampler tables                                                            */
+/* ------------------------------------------------------------------------ */
+typedef struct cgb_sampler_desc {
+    /* inverse-CDF table of generate_particle_radii (utils.py:159-164):
+       P_r = [0, m[:ridx]] / m[ridx-1],  r = [0, r[:ridx]] */
+    const double *d_cdf_P;
+    const double *d_cdf_r;
+    int32_t n_cdf;
+    /* energy_spline = IUS(radius, psi) (virial.py:152): knots [n_psi+4], coeffs [n_psi] */
+    int32_t n_psi;
+    const double *d_psi_t;
+    const double *d_psi_c;
+    /* f(E) spline self.f (virial.py:67): knots [n_f+4], coeffs [n_f]; may be NULL for
+       a position-only sampler (gas / tracer) */
+    const double *d_f_t;
+    const double *d_f_c;
+    int32_t n_f;
+    /* number of buckets of the fp32 screening table (power of two, 0 = default) */
+    int32_t n_buckets;
+    /* optional extra radial splines evaluated at the drawn radius (gas:
+       thermal energy model.py:908-916, density model.py:921-930); same knot layout */
+    int32_t n_aux;      /* 0, 1 or 2 */
+    int32_t n_aux_coef; /* coefficients per aux spline */
+    const double *d_aux_t[2];
+    const double *d_aux_c[2];
+} cgb_sampler_desc;
+
+size_t cgb_sampler_workspace_bytes(const cgb_sampler_desc *desc);
+/* Builds the derived device tables (CDF slopes, piecewise-polynomial forms, fp32
+ * screening bounds) into the caller's workspace.  Asynchronous. */
+int cgb_sampler_prepare(const cgb_sampler_desc *desc, void *d_workspace, size_t workspace_bytes,
+                        void *stream);
+
+/* Host-supplied uniforms (parity mode); all nullable, indexed by LOCAL particle
+ * index (id - id_begin).  When a pointer is NULL the Philox stream is used. */
+typedef struct cgb_host_uniforms {
+    const double *d_u_r;    /* draw #1 utils.py:161            */
+    const double *d_u_ct;   /* draw #2 virial.py:175 (u of uniform(-1,1) = -1+2u) */
+    const double *d_u_ph;   /* draw #3 virial.py:176           */
+    const double *d_u_ctv;  /* draw #4 virial.py:213           */
+    const double *d_u_phv;  /* draw #5 virial.py:214           */
+    const double *d_u_trial; /* [n_local][t_cap][2] (u1,u2) per trial, mode B literal */
+    int64_t t_cap;
+} cgb_host_uniforms;
+
+#define CGB_NMOMENTS 16
+/* moments[ 0] particles           [ 1] sum trials        [ 2] max trials
+ *        [ 3] sum v^2             [ 4] sum psi           [ 5..7] sum x,y,z
+ *        [ 8..10] sum vx,vy,vz    [11] non-positive envelopes
+ *        [12] particles finished cooperatively (> lane cap)  [13] failures (trial cap)
+ *        [14] sum r               [15] exact (fp64) spline evaluations in the trial loop */
+
+typedef struct cgb_sample_args {
+    const void *d_workspace; /* prepared by cgb_sampler_prepare */
+    int64_t id_begin;        /* global index range [id_begin, id_end) generated by this call */
+    int64_t id_end;
+    double particle_mass;    /* mtot / num_particles (virial.py:225-227) */
+    uint64_t seed;
+    int32_t out_dtype;       /* CGB_DTYPE_F64 / CGB_DTYPE_F32 for pos/vel/mass/pot */
+    int32_t flags;           /* reserved, 0 */
+    /* outputs, local index = id - id_begin; pos/vel are (3, ld) plane-major ("SoA":
+       the memory layout of unyt_array([x,y,z]).T, virial.py:180-187,216-223) */
+    void *d_pos;
+    void *d_vel;
+    int64_t ld;              /* plane stride in elements (>= id_end - id_begin) */
+    void *d_mass;            /* nullable */
+    void *d_pot;             /* nullable: particle_potential = -psi (virial.py:229-234) */
+    double *d_radius;        /* nullable, always f64 */
+    double *d_speed;         /* nullable, always f64 */
+    int32_t *d_trials;       /* nullable */
+    double *d_moments;       /* nullable, CGB_NMOMENTS doubles, ACCUMULATED (caller zeroes) */
+    cgb_host_uniforms hu;
+} cgb_sample_args;
+
+/* P+R+E+V fused: replaces VirialEquilibrium.generate_particles (virial.py:108-236)
+ * for sub_sample == 1: radius draw (utils.py:154-166), psi / envelope
+ * (virial.py:191-194), rejection-sampled speed (the absent opt/cython_utils.pyx
+ * generate_velocities, call site virial.py:198-206), isotropic directions and the
+ * SoA field stores.  d_tile_counter: one zero-initialised device int64 used for
+ * dynamic tile scheduling (caller zeroes before each call). */
+int cgb_sample_particles(const cgb_sample_args *args, int64_t *d_tile_counter, void *stream);
+
+/* Directions-only pass used for sub_sample > 1 (virial.py:170-176,208-223): particle
+ * i takes radius/speed d_radius_sub[i % n_sub], d_speed_sub[i % n_sub] and fresh
+ * directions; d_psi_sub (nullable) feeds the potential. */
+int cgb_assemble_particles(const cgb_sample_args *args, const double *d_radius_sub,
+                           const double *d_speed_sub, const double *d_psi_sub, int64_t n_sub,
+                           void *stream);
+
+/* V: mirror of the Cython seam generate_velocities(psi, vesc, fv2esc, knots, coeffs,
+ * k, quiet) -> float64[n]  (call site virial.py:198-206).  knots = t[k:-k]
+ * (get_knots()), coeffs = c[:n_coeffs] (get_coeffs()), k must be 3.
+ * d_u_trial (nullable) = [n][t_cap][2] host-supplied uniforms, else Philox stream
+ * CGB_STREAM_VEL_TRIAL with ids first_id + i.  d_trials (nullable): accepted trial
+ * count, -1 where no trial within t_cap accepted (speed = NaN there).
+ * d_work: >= cgb_generate_velocities_workspace_bytes(n_coeffs). */
+size_t cgb_generate_velocities_workspace_bytes(int n_coeffs);
+int cgb_generate_velocities(const double *d_psi, const double *d_vesc, const double *d_fv2esc,
+                            const double *d_knots, int n_knots, const double *d_coeffs,
+                            int n_coeffs, int k, const double *d_u_trial, int64_t t_cap,
+                            uint64_t seed, int64_t first_id, double *d_vel, int32_t *d_trials,
+                            int64_t n, void *d_work, size_t work_bytes, void *stream);
+
+/* Gs: replaces the numeric part of ClusterModel.generate_gas_particles
+ * (model.py:838-947) and generate_tracer_particles (model.py:766-836): radius from
+ * the gas-mass CDF, isotropic position, aux splines (thermal energy, density) and
+ * optional potential at the radius; velocity planes are zero-filled when d_vel != NULL.
+ * d_aux_out[k]: nullable f64/f32 arrays (out_dtype) for aux spline k. */
+int cgb_sample_gas(const cgb_sample_args *args, void *d_aux_out0, void *d_aux_out1, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CGB200_H */

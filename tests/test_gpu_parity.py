@@ -1,0 +1,393 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle.
+
+Tolerances are BASELINE.json's: f(E) rtol 1e-8; coordinates on identical uniforms
+fp64 rtol 1e-10 (+ atol 1e-12 * |r| resp. |v| for components that nearly vanish,
+SURVEY.md section 7 hard part 5), fp32 rtol 1e-5; accept/reject decisions exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests.configs import assert_tables_equal, oracle_model, product_model
+
+pytestmark = pytest.mark.gpu
+
+RTOL64 = 1e-10
+RTOL32 = 1e-5
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _vec_close(a, b, rtol, scale):
+    """|a-b| <= rtol*|b| + 1e-12*scale (scale = |r| or |v| per particle)."""
+    atol = (1e-12 if rtol < 1e-6 else 1e-7) * scale[:, None]
+    bad = np.abs(a - b) > rtol * np.abs(b) + atol
+    assert not bad.any(), f"{bad.sum()} components differ, worst {np.abs(a - b)[bad].max()}"
+
+
+# --------------------------------------------------------------------------- #
+# splines
+# --------------------------------------------------------------------------- #
+def test_spline_fit_and_eval_match_fitpack():
+    from scipy.interpolate import InterpolatedUnivariateSpline as IUS
+
+    from cluster_generator_b200.virial import DeviceSpline
+
+    om = oracle_model("hernquist")
+    x = -om["gravitational_potential"][::-1]
+    y = om["dark_matter_density"][::-1]
+    s_ref = IUS(x, y)
+    s = DeviceSpline.fit(x, y)
+    t, c, k = s._eval_args
+    np.testing.assert_array_equal(t, s_ref._eval_args[0])
+    np.testing.assert_allclose(c, s_ref.get_coeffs(), rtol=1e-12)
+    np.testing.assert_array_equal(s.get_knots(), s_ref.get_knots())
+    xx = np.concatenate([np.linspace(0.0, x[0], 50), np.random.RandomState(0).uniform(x[0], x[-1], 5000),
+                         np.linspace(x[-1], 1.1 * x[-1], 20)])
+    np.testing.assert_allclose(s(xx), s_ref(xx), rtol=1e-10)
+    np.testing.assert_allclose(s(xx, 1), s_ref(xx, 1), rtol=1e-9)
+
+
+def test_spline_rejects_non_increasing_x():
+    from cluster_generator_b200.virial import DeviceSpline
+
+    with pytest.raises(ValueError):
+        DeviceSpline.fit(np.array([0.0, 1.0, 1.0, 2.0, 3.0]), np.zeros(5))
+
+
+# --------------------------------------------------------------------------- #
+# D: Eddington f(E)
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("name,ptype", [("hernquist", "dark_matter"), ("nfw_bcg", "dark_matter"),
+                                        ("nfw_bcg", "stellar"), ("vikhlinin", "dark_matter")])
+def test_eddington_df_matches_reference_arithmetic(oracle, name, ptype):
+    om, pm = oracle_model(name), product_model(name)
+    assert_tables_equal(om, pm)
+    ov = oracle.VirialEquilibrium(om, ptype)      # scipy quad + FITPACK, as virial.py:43-68
+    pv = pm.dm_virial if ptype == "dark_matter" else pm.star_virial
+    np.testing.assert_allclose(pv.g, ov.g, rtol=1e-9)
+    np.testing.assert_allclose(pv.df.d, ov.df, rtol=1e-8)          # north_star: f(E) rtol 1e-8
+    np.testing.assert_allclose(pv.ff, ov.ff, rtol=1e-8)
+    # decision-for-decision: sub-interval counts equal the C QAGS restatement's
+    import ctypes
+    from scipy.interpolate import InterpolatedUnivariateSpline as IUS
+    ee = np.ascontiguousarray(ov.ee)
+    t, c, _ = IUS(ee, om[f"{ptype}_density"][::-1])._eval_args
+    t, c = np.ascontiguousarray(t), np.ascontiguousarray(c[: ee.size])
+    g = np.empty(ee.size)
+    last = np.zeros(ee.size, dtype=np.int32)
+    ier = np.zeros(ee.size, dtype=np.int32)
+    ip = ctypes.POINTER(ctypes.c_int)
+    oracle.clib().cgo_eddington_g(oracle._dptr(ee), ee.size, oracle._dptr(t), oracle._dptr(c), 1.49e-5,
+                                  1.49e-5, oracle._dptr(g), last.ctypes.data_as(ip), ier.ctypes.data_as(ip))
+    np.testing.assert_array_equal(g, ov.g)   # the C restatement is bit-equal to scipy
+    assert (pv.qags_last != last).sum() <= 2  # device: same decisions (fit coefficients differ ~1e-15)
+    np.testing.assert_array_equal(pv.qags_ier, ier)
+
+
+def test_eddington_df_supplied(oracle):
+    om, pm = oracle_model("hernquist"), product_model("hernquist")
+    from cluster_generator_b200 import VirialEquilibrium
+
+    ov = oracle.VirialEquilibrium(om, "dark_matter")
+    pv = VirialEquilibrium(pm, "dark_matter", df=ov.df)
+    x = np.linspace(0.01, ov.ee[-1], 1000)
+    np.testing.assert_allclose(pv.f(x), ov.f(x), rtol=1e-10)
+
+
+# --------------------------------------------------------------------------- #
+# C: check_virial
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("name", ["hernquist", "nfw_bcg"])
+def test_check_virial_matches_reference_arithmetic(oracle, name):
+    import ctypes
+
+    om, pm = oracle_model(name), product_model(name)
+    ov = oracle.VirialEquilibrium(om, "dark_matter")
+    pv = pm.dm_virial
+    rho, chk = pv.check_virial()
+    # oracle: C restatement (bit-equal to scipy's quad, see tests/test_oracle_cpu.py) on
+    # the oracle's own f spline
+    ee = np.ascontiguousarray(ov.ee)
+    t, c, _ = ov.f._eval_args
+    t, c = np.ascontiguousarray(t), np.ascontiguousarray(c[: ee.size])
+    rho_o = np.empty(ee.size)
+    oracle.clib().cgo_check_virial_rho(oracle._dptr(ee), ee.size, oracle._dptr(t), oracle._dptr(c),
+                                       oracle._dptr(rho_o), None, None)
+    rho_o = rho_o[::-1]
+    chk_o = (rho_o - om["dark_matter_density"]) / om["dark_matter_density"]
+    np.testing.assert_allclose(rho, rho_o, rtol=1e-6)       # residual array rtol 1e-6
+    np.testing.assert_allclose(chk, chk_o, rtol=1e-5, atol=1e-9)
+    assert np.all(chk < 1e-4)                               # test_models.py:127-130 (signed)
+
+
+# --------------------------------------------------------------------------- #
+# V: the Cython seam mirror
+# --------------------------------------------------------------------------- #
+def _seam_inputs(oracle, name, ptype, n, seed=11):
+    om = oracle_model(name)
+    ov = om.dm_virial if ptype == "dark_matter" else om.star_virial
+    u = oracle.device_rng_uniforms(seed, 0, n)
+    ov.generate_particles(n, uniforms=u,
+                          velocity_fn=lambda *a: oracle.generate_velocities_counter(*a, seed=seed))
+    return ov, ov.last, ov.last_trials
+
+
+def _call_seam(ov, last, n, seed, u_trial=None, first_id=0):
+    from cluster_generator_b200 import _native as N
+
+    dev = N.require_cuda()
+    knots, coeffs = ov.f.get_knots(), ov.f.get_coeffs()
+    psi, vesc, env = (N.dev_f64(last[k]) for k in ("psi", "vesc", "fv2esc"))
+    kd, cd = N.dev_f64(knots), N.dev_f64(coeffs)
+    vel = torch.empty(n, dtype=torch.float64, device=dev)
+    trials = torch.empty(n, dtype=torch.int32, device=dev)
+    nb = N.lib().cgb_generate_velocities_workspace_bytes(coeffs.size)
+    work = N.workspace(nb)
+    ut = None if u_trial is None else N.dev_f64(u_trial)
+    tcap = 0 if u_trial is None else u_trial.shape[1]
+    N.check(N.lib().cgb_generate_velocities(N.ptr(psi), N.ptr(vesc), N.ptr(env), N.ptr(kd), knots.size,
+                                            N.ptr(cd), coeffs.size, 3, N.ptr(ut), tcap, seed, first_id,
+                                            N.ptr(vel), N.ptr(trials), n, N.ptr(work), nb, N.stream_ptr()))
+    return _np(vel), _np(trials)
+
+
+@pytest.mark.parametrize("name,ptype,n", [("hernquist", "dark_matter", 100_000),
+                                          ("nfw_bcg", "stellar", 20_000)])
+def test_generate_velocities_counter_mode_exact(oracle, name, ptype, n):
+    ov, last, trials_o = _seam_inputs(oracle, name, ptype, n)
+    vel, trials = _call_seam(ov, last, n, 11)
+    np.testing.assert_array_equal(trials, trials_o)          # accept/reject decisions identical
+    np.testing.assert_allclose(vel, last["speed"], rtol=RTOL64)
+
+
+def test_generate_velocities_host_uniform_array(oracle):
+    n, tcap = 4000, 600
+    ov, last, _ = _seam_inputs(oracle, "hernquist", "dark_matter", n)
+    u = np.random.RandomState(3).uniform(size=(n, tcap, 2))
+    vel_o, tr_o = oracle.generate_velocities_array(last["psi"], last["vesc"], last["fv2esc"],
+                                                   ov.f.get_knots(), ov.f.get_coeffs(), 3, u)
+    vel, tr = _call_seam(ov, last, n, 0, u_trial=u)
+    np.testing.assert_array_equal(tr, tr_o)
+    ok = tr_o > 0
+    assert ok.sum() > 0.9 * n and (~ok).sum() > 0             # both accepted and capped cases seen
+    np.testing.assert_allclose(vel[ok], vel_o[ok], rtol=RTOL64)
+    assert np.isnan(vel[~ok]).all()
+
+
+def test_generate_velocities_rejects_bad_arguments():
+    from cluster_generator_b200 import _native as N
+
+    w = N.workspace(1 << 20)
+    d = torch.zeros(1000, dtype=torch.float64, device="cuda")
+    rc = N.lib().cgb_generate_velocities(N.ptr(d), N.ptr(d), N.ptr(d), N.ptr(d), 998, N.ptr(d), 1000, 2,
+                                         None, 0, 0, 0, N.ptr(d), None, 10, N.ptr(w), 1 << 20, None)
+    with pytest.raises(ValueError, match="k=3"):
+        N.check(rc)
+
+
+# --------------------------------------------------------------------------- #
+# P: fused sampler
+# --------------------------------------------------------------------------- #
+def _oracle_particles(oracle, name, ptype, n, seed, **kw):
+    om = oracle_model(name)
+    ov = om.dm_virial if ptype == "dark_matter" else om.star_virial
+    u = oracle.device_rng_uniforms(seed, 0, n)
+    f = ov.generate_particles(n, uniforms=u,
+                              velocity_fn=lambda *a: oracle.generate_velocities_counter(*a, seed=seed), **kw)
+    return ov, f
+
+
+def _device_particles(name, ptype, n, seed, **kw):
+    """Device-RNG run with an explicit Philox seed (bypassing the prng->seed draw)."""
+    import cluster_generator_b200.virial as V
+
+    pm = product_model(name)
+    pv = pm.dm_virial if ptype == "dark_matter" else pm.star_virial
+    orig = V.seed_from_prng
+    V.seed_from_prng = lambda prng, species: seed
+    try:
+        return pv, pv.generate_particles(n, prng=0, **kw)
+    finally:
+        V.seed_from_prng = orig
+
+
+@pytest.mark.parametrize("name,ptype,n", [("hernquist", "dark_matter", 100_000),
+                                          ("nfw_bcg", "dark_matter", 50_000),
+                                          ("nfw_bcg", "stellar", 20_000),
+                                          ("vikhlinin", "dark_matter", 50_000)])
+def test_fused_sampler_matches_oracle_on_identical_uniforms(oracle, name, ptype, n):
+    key = {"dark_matter": "dm", "stellar": "star"}[ptype]
+    ov, fo = _oracle_particles(oracle, name, ptype, n, 77, compute_potential=True)
+    pv, p = _device_particles(name, ptype, n, 77, compute_potential=True)
+    pos, vel = _np(p[key, "particle_position"]), _np(p[key, "particle_velocity"])
+    assert pos.shape == (n, 3) and pos.strides == (8, 8 * n)      # SoA planes behind (n,3)
+    r_o = ov.last["radius"]
+    _vec_close(pos, fo[key, "particle_position"], RTOL64, r_o)
+    _vec_close(vel, fo[key, "particle_velocity"], RTOL64, ov.last["speed"])
+    np.testing.assert_allclose(np.linalg.norm(vel, axis=1), ov.last["speed"], rtol=1e-9)
+    np.testing.assert_allclose(_np(p[key, "particle_mass"]), fo[key, "particle_mass"], rtol=1e-15)
+    np.testing.assert_allclose(_np(p[key, "particle_potential"]), fo[key, "particle_potential"], rtol=RTOL64)
+    d = p.diagnostics[key].as_dict()
+    assert d["particles"] == n and d["failures"] == 0
+    assert d["sum_trials"] == ov.last_trials.sum()                # every accept/reject decision
+    assert d["max_trials"] == ov.last_trials.max()
+    assert d["exact_evaluations"] < 0.05 * d["sum_trials"]        # the fp32 screen does the work
+
+
+def test_fused_sampler_numpy_rng_reproduces_reference_draw_order(oracle):
+    """rng='numpy': radii, positions and velocity directions come from the caller's
+    RandomState in the reference's draw order (virial.py:162,175-176,213-214)."""
+    from cluster_generator_b200.virial import PRIVATE_TRIAL_SEED
+
+    n = 30_000
+    om, pm = oracle_model("hernquist"), product_model("hernquist")
+    ov = om.dm_virial
+    fo = ov.generate_particles(
+        n, prng=25,
+        velocity_fn=lambda *a: oracle.generate_velocities_counter(*a, seed=PRIVATE_TRIAL_SEED))
+    p = pm.generate_dm_particles(n, prng=25, rng="numpy")
+    _vec_close(_np(p["dm", "particle_position"]), fo["dm", "particle_position"], RTOL64, ov.last["radius"])
+    _vec_close(_np(p["dm", "particle_velocity"]), fo["dm", "particle_velocity"], RTOL64, ov.last["speed"])
+
+
+def test_fused_sampler_fp32_outputs(oracle):
+    n = 50_000
+    ov, fo = _oracle_particles(oracle, "hernquist", "dark_matter", n, 5)
+    pv, p = _device_particles("hernquist", "dark_matter", n, 5, dtype=torch.float32)
+    pos = _np(p["dm", "particle_position"])
+    assert pos.dtype == np.float32
+    _vec_close(pos.astype(np.float64), fo["dm", "particle_position"], RTOL32, ov.last["radius"])
+    _vec_close(_np(p["dm", "particle_velocity"]).astype(np.float64), fo["dm", "particle_velocity"], RTOL32,
+               ov.last["speed"])
+    assert p.diagnostics["dm"].as_dict()["sum_trials"] == ov.last_trials.sum()   # decisions stay fp64-exact
+
+
+def test_sharded_generation_is_bit_identical():
+    n = 100_003
+    _, full = _device_particles("hernquist", "dark_matter", n, 9)
+    parts = [_device_particles("hernquist", "dark_matter", n, 9, shard=(k, 3))[1] for k in range(3)]
+    for f in ("particle_position", "particle_velocity", "particle_mass"):
+        cat = torch.cat([q["dm", f] for q in parts])
+        assert torch.equal(cat, full["dm", f]), f
+    tot = sum(q.diagnostics["dm"].as_dict()["sum_trials"] for q in parts)
+    assert tot == full.diagnostics["dm"].as_dict()["sum_trials"]
+
+
+def test_sub_sample_tiles_radius_and_speed(oracle):
+    n, s = 40_000, 4
+    ov, fo = _oracle_particles(oracle, "hernquist", "dark_matter", n, 21, sub_sample=s, compute_potential=True)
+    pv, p = _device_particles("hernquist", "dark_matter", n, 21, sub_sample=s, compute_potential=True)
+    r_o = np.tile(ov.last["radius"][: n // s], s)
+    _vec_close(_np(p["dm", "particle_position"]), fo["dm", "particle_position"], RTOL64, r_o)
+    _vec_close(_np(p["dm", "particle_velocity"]), fo["dm", "particle_velocity"], RTOL64, ov.last["speed"])
+    np.testing.assert_allclose(_np(p["dm", "particle_potential"]), fo["dm", "particle_potential"], rtol=RTOL64)
+    with pytest.raises(ValueError):
+        pv.generate_particles(10, sub_sample=3)
+
+
+def test_r_max_and_edge_counts(oracle):
+    om, pm = oracle_model("hernquist"), product_model("hernquist")
+    for n in (0, 1, 31, 257):
+        p = pm.generate_dm_particles(n, prng=1)
+        assert p.num_particles["dm"] == n and p["dm", "particle_position"].shape == (n, 3)
+    ov, fo = _oracle_particles(oracle, "hernquist", "dark_matter", 20_000, 4, r_max=2000.0)
+    pv, p = _device_particles("hernquist", "dark_matter", 20_000, 4, r_max=2000.0)
+    pos = _np(p["dm", "particle_position"])
+    _vec_close(pos, fo["dm", "particle_position"], RTOL64, ov.last["radius"])
+    assert np.linalg.norm(pos, axis=1).max() < 2000.0
+    np.testing.assert_allclose(_np(p["dm", "particle_mass"]), fo["dm", "particle_mass"], rtol=1e-15)
+
+
+def test_non_monotone_potential_raises_like_the_reference():
+    import cluster_generator_b200 as cg
+
+    pm = product_model("hernquist")
+    fields = {k: np.array(v) for k, v in pm.fields.items()}
+    fields["gravitational_potential"][500] = fields["gravitational_potential"][499]
+    bad = cg.ClusterModel.from_arrays(fields)
+    with pytest.raises(ValueError, match="increasing"):
+        bad.dm_virial
+
+
+# --------------------------------------------------------------------------- #
+# Gs: gas particles
+# --------------------------------------------------------------------------- #
+def test_gas_particles_match_oracle(oracle):
+    n = 100_000
+    om, pm = oracle_model("vikhlinin"), product_model("vikhlinin")
+    fo = oracle.generate_gas_particles(om, n, prng=25, compute_potential=True)
+    p = pm.generate_gas_particles(n, prng=25, rng="numpy", compute_potential=True)
+    pos = _np(p["gas", "particle_position"])
+    _vec_close(pos, fo["gas", "particle_position"], RTOL64, np.linalg.norm(fo["gas", "particle_position"], axis=1))
+    for f in ("thermal_energy", "density", "particle_mass", "particle_potential"):
+        np.testing.assert_allclose(_np(p["gas", f]), fo["gas", f], rtol=1e-9, err_msg=f)
+    assert torch.count_nonzero(p["gas", "particle_velocity"]) == 0
+    assert p.num_particles["gas"] == n
+
+
+# --------------------------------------------------------------------------- #
+# reference test-suite invariants (tests/test_particles.py:95-186)
+# --------------------------------------------------------------------------- #
+def test_reference_particle_invariants():
+    pm = product_model("nfw_bcg")
+    prng = np.random.RandomState(25)
+    dm = pm.generate_dm_particles(1000, prng=prng)
+    st = pm.generate_star_particles(1000, prng=prng)
+    assert dm.num_particles["dm"] == 1000 and st.num_particles["star"] == 1000
+    allp = dm + st
+    assert allp.num_particles == {"dm": 1000, "star": 1000}
+    for pt in ("dm", "star"):
+        for f in ("particle_position", "particle_velocity", "particle_mass"):
+            assert torch.isfinite(allp[pt, f]).all()
+        assert (allp[pt, "particle_mass"] > 0).all()
+        assert torch.linalg.norm(allp[pt, "particle_position"], dim=1).max() < 50_000
+    both = dm + dm
+    assert both.num_particles["dm"] == 2000 and both["dm", "particle_position"].shape == (2000, 3)
+    dm.add_offsets([100.0, 0.0, 0.0], [0.0, 1.0, 0.0])
+
+
+# --------------------------------------------------------------------------- #
+# statistics with the device RNG (KS on r, |v|, E)
+# --------------------------------------------------------------------------- #
+def test_device_rng_is_statistically_indistinguishable_from_oracle(oracle):
+    from scipy.stats import ks_2samp
+
+    n = 1_000_000
+    om, pm = oracle_model("hernquist"), product_model("hernquist")
+    ov = om.dm_virial
+    fo = ov.generate_particles(n, prng=123)          # mode A: independent sequential stream
+    p = pm.generate_dm_particles(n, prng=456, compute_potential=True)
+    pos, vel = _np(p["dm", "particle_position"]), _np(p["dm", "particle_velocity"])
+    r, v = np.linalg.norm(pos, axis=1), np.linalg.norm(vel, axis=1)
+    E = -_np(p["dm", "particle_potential"]) - 0.5 * v * v
+    E_o = ov.last["psi"] - 0.5 * ov.last["speed"] ** 2
+    for a, b, what in ((r, ov.last["radius"], "r"), (v, ov.last["speed"], "|v|"), (E, E_o, "E")):
+        assert ks_2samp(a, b).pvalue > 0.01, what
+    # isotropy
+    assert abs((pos[:, 2] / r).mean()) < 4 / np.sqrt(3 * n)
+    assert abs(np.arctan2(pos[:, 1], pos[:, 0]).mean()) < 4 * np.pi / np.sqrt(3 * n)
+    assert (E > 0).all()                              # bound particles only
+
+
+def test_full_size_properties_config2():
+    """BASELINE config 2 at full size (1e7 DM): size-independent properties."""
+    n = 10_000_000
+    pm = product_model("vikhlinin")
+    p = pm.generate_dm_particles(n, prng=7, compute_potential=True)
+    d = p.diagnostics["dm"].as_dict()
+    assert d["particles"] == n and d["failures"] == 0
+    assert 5.0 < d["mean_trials"] < 30.0              # SURVEY: T-bar ~ 11.7
+    pos, vel = p["dm", "particle_position"], p["dm", "particle_velocity"]
+    assert torch.isfinite(pos).all() and torch.isfinite(vel).all()
+    r = torch.linalg.norm(pos, dim=1)
+    assert r.max() < 1.0e4 * (1 + 1e-12)
+    E = -p["dm", "particle_potential"] - 0.5 * (vel * vel).sum(dim=1)
+    assert (E > 0).all()
+    m = p["dm", "particle_mass"]
+    np.testing.assert_allclose(float(m.sum()), pm.dm_virial.sampler_tables().mtot, rtol=1e-9)
+    # idempotence: same prng -> same particles
+    q = pm.generate_dm_particles(n, prng=7)
+    assert torch.equal(q["dm", "particle_position"], pos)

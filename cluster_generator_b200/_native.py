@@ -73,6 +73,8 @@ SYMBOLS = [
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     ("cgb_check_virial", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p]),
+    ("cgb_qags_trace", c_int, [c_void_p, c_void_p, c_int, c_double, c_double, c_double, c_double,
+                               c_double, c_int, c_void_p, c_void_p]),
     ("cgb_sampler_workspace_bytes", c_size_t, [POINTER(SamplerDesc)]),
     ("cgb_sampler_prepare", c_int, [POINTER(SamplerDesc), c_void_p, c_size_t, c_void_p]),
     ("cgb_sample_particles", c_int, [POINTER(SampleArgs), c_void_p, c_void_p]),

@@ -70,6 +70,20 @@ struct RhoIntegrand {
     }
 };
 
+// x^1.5 rounded to nearest (error < 0.5 ulp + 2^-100): sqrt residual and product in
+// double-double with explicit FMAs.  QUADPACK computes this with libm pow (glibc: < 0.52
+// ulp), so the two agree except in rare near-tie cases; CUDA's pow (2 ulp) would not.
+__device__ __forceinline__ double pow15(double x)
+{
+    const double s = sqrt(x);
+    const double r = fma(-s, s, x);      // x - s*s, exact
+    const double c = r / (2.0 * s);      // sqrt(x) = s + c
+    const double hi = x * s;
+    double lo = fma(x, s, -hi);          // x*s = hi + lo, exact
+    lo = fma(x, c, lo);
+    return hi + lo;
+}
+
 // Warp-cooperative dqk21.  All lanes return identical values.
 template <class F>
 __device__ __forceinline__ void dqk21_warp(const F& f, double a, double b, double& result,
@@ -126,7 +140,7 @@ __device__ __forceinline__ void dqk21_warp(const F& f, double a, double b, doubl
     resasc *= dhlgth;
     abserr = fabs((resk - resg) * hlgth);
     if (resasc != 0.0 && abserr != 0.0) {
-        const double r = pow(200.0 * abserr / resasc, 1.5);
+        const double r = pow15(200.0 * abserr / resasc);
         abserr = resasc * (r < 1.0 ? r : 1.0);
     }
     if (resabs > UFLOW / (50.0 * EPMACH)) {
@@ -541,6 +555,72 @@ __global__ void cgb_ff_kernel(const double* __restrict__ t, const double* __rest
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     ff[i] = cgb_splder1(t, n + 4, wrk, ee[i]) / inv_norm_den;
+}
+
+// One integral, with the full QAGS state dumped: out = [result, abserr, last, ier,
+// alist[50], blist[50], rlist[50], elist[50]].  kind 0: dgdp integrand of the density
+// spline (t, c) with e = par; kind 1: rho_int integrand of the f spline with psi = par.
+__global__ void __launch_bounds__(32)
+cgb_qags_trace_kernel(const double* __restrict__ t, const double* __restrict__ c, int n, double par,
+                      double a, double b, double epsabs, double epsrel, int kind,
+                      double* __restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int nk = n + 4;
+    double* s_t = (double*)smem;
+    double* s_c = s_t + nk;
+    QagsScratch* scr = (QagsScratch*)(s_c + n);
+    for (int i = threadIdx.x; i < nk; i += 32) s_t[i] = t[i];
+    for (int i = threadIdx.x; i < n; i += 32) {
+        if (kind == 0) {
+            double w = 0.0;
+            if (i < n - 1) {
+                const double fac = t[i + 4] - t[i + 1];
+                w = (fac > 0.0) ? 3.0 * (c[i + 1] - c[i]) / fac : 0.0;
+            }
+            s_c[i] = w;
+        } else {
+            s_c[i] = c[i];
+        }
+    }
+    __syncthreads();
+    double result, abserr;
+    int last, ier;
+    if (kind == 0) {
+        DgdpIntegrand f;
+        f.t = s_t; f.wrk = s_c; f.nk = nk; f.e = par;
+        ier = dqagse_warp(f, a, b, epsabs, epsrel, QAGS_LIMIT, scr[0], result, abserr, last);
+    } else {
+        RhoIntegrand f;
+        f.t = s_t; f.c = s_c; f.nk = nk; f.psi = par;
+        ier = dqagse_warp(f, a, b, epsabs, epsrel, QAGS_LIMIT, scr[0], result, abserr, last);
+    }
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        out[0] = result; out[1] = abserr; out[2] = (double)last; out[3] = (double)ier;
+        for (int i = 0; i < QAGS_LIMIT; ++i) {
+            out[4 + i] = scr[0].alist[i];
+            out[4 + QAGS_LIMIT + i] = scr[0].blist[i];
+            out[4 + 2 * QAGS_LIMIT + i] = scr[0].rlist[i];
+            out[4 + 3 * QAGS_LIMIT + i] = scr[0].elist[i];
+        }
+    }
+}
+
+extern "C" int cgb_qags_trace(const double* d_t, const double* d_c, int n, double par, double a,
+                              double b, double epsabs, double epsrel, int kind, double* d_out,
+                              void* stream)
+{
+    CGB_REQUIRE(n >= 4 && d_t && d_c && d_out, "cgb_qags_trace: bad arguments");
+    CGB_REQUIRE(kind == 0 || kind == 1, "cgb_qags_trace: kind must be 0 or 1");
+    const size_t smem = (size_t)(2 * n + 4) * sizeof(double) + sizeof(QagsScratch);
+    CGB_REQUIRE(smem <= 227 * 1024, "cgb_qags_trace: n = %d needs %zu B of shared memory", n, smem);
+    CGB_CUDA_CHECK(cudaFuncSetAttribute(cgb_qags_trace_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cgb_qags_trace_kernel<<<1, 32, smem, (cudaStream_t)stream>>>(d_t, d_c, n, par, a, b, epsabs, epsrel,
+                                                                kind, d_out);
+    CGB_CUDA_CHECK(cudaGetLastError());
+    return CGB_OK;
 }
 
 static size_t edd_smem_bytes(int n)

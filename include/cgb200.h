@@ -109,6 +109,15 @@ int cgb_check_virial(const double *d_ee, const double *d_pden, int n, const doub
                      const double *d_f_c, double *d_rho, double *d_chk, int *d_last, int *d_ier,
                      void *stream);
 
+/* Diagnostic: ONE QAGS integral with its full adaptive state, so tests can compare
+ * the device quadrature decision for decision with QUADPACK (scipy's
+ * quad(..., full_output=1): last, alist, blist, rlist, elist).
+ * kind 0: integrand 2*rho'(par - t^2) of the density spline (d_t, d_c)  (virial.py:47)
+ * kind 1: integrand f(e) sqrt(2 (par - e)) of the f spline (d_t, d_c)   (virial.py:96)
+ * d_out[4 + 4*50] = result, abserr, last, ier, alist[50], blist[50], rlist[50], elist[50]. */
+int cgb_qags_trace(const double *d_t, const double *d_c, int n, double par, double a, double b,
+                   double epsabs, double epsrel, int kind, double *d_out, void *stream);
+
 /* ------------------------------------------------------------------------ */
 /* Sampler tables                                                            */
 /* ------------------------------------------------------------------------ */

@@ -360,7 +360,8 @@ class VirialEquilibrium:
         nonzero = self.model[density] > 0.0
         radius_sub, mtot = generate_particle_radii(
             self.model["radius"][nonzero], self.model[mass][nonzero], num_particles_sub,
-            r_max=r_max, prng=prng, u=None if uniforms is None else uniforms["u_r"],
+            r_max=r_max, prng=prng,
+            u=None if uniforms is None else np.asarray(uniforms["u_r"])[:num_particles_sub],
         )
         radius = np.tile(radius_sub, sub_sample)[:num_particles] if sub_sample > 1 else radius_sub
 

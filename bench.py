@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""
+bench.py -- particles/sec of the particle-sampling hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # CUDA arm (this repo)
+  python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port of the
+                                                           # reference's own CPU path
+
+Workload (BASELINE.json configs[1]): Vikhlinin
+density+temperature hydrostatic model, 1e7 DM particles (positions + velocities + mass,
+Eddington f(E) + rejection sampling) plus 1e7 gas particles (positions, zero velocity,
+mass, thermal energy, density) per GPU.  One "step" = one pass of both generators with
+the tables resident in HBM.  Weak scaling: rank k of N generates the k-th contiguous
+index shard of N * 1e7 particles per species; no data-path collective (the only
+collective, an all-reduce of the 16 moment words, is included in the timed region).
+
+Prints ONE JSON line (rank 0).  Timing: CUDA events on the launching stream, barrier +
+synchronize on both sides, max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_PER_GPU = 10_000_000
+WORKLOAD = "vikhlinin_dens_temp_hse: 1e7 DM (pos+vel+mass) + 1e7 gas (pos+vel0+mass+e+rho) per GPU, fp64"
+METRIC = "particles/sec (pos+vel, device-timed)"
+UNIT = "particles/s"
+F_FIXED, F_TRIAL = 200.0, 52.0   # algorithmic flop per DM particle = 200 + 52 * T
+B_DM, B_GAS = 56.0, 72.0         # algorithmic bytes written per particle (fp64)
+
+
+def build_product_model():
+    import cluster_generator_b200 as cg
+
+    dens = cg.vikhlinin_density_profile(4.2e5, 100.0, 1000.0, 1.0, 0.67, 3.0)
+    temp = cg.vikhlinin_temperature_profile(10.0, 0.0, 2.0, 1.0, 1500.0, 6.0, 80.0, 1.0)
+    return cg.ClusterModel.from_dens_and_temp(0.1, 1.0e4, dens, temp)
+
+
+def build_oracle_model():
+    from oracle import cg_oracle as O
+
+    dens = O.vikhlinin_density_profile(4.2e5, 100.0, 1000.0, 1.0, 0.67, 3.0)
+    temp = O.vikhlinin_temperature_profile(10.0, 0.0, 2.0, 1.0, 1500.0, 6.0, 80.0, 1.0)
+    return O.from_dens_and_temp(0.1, 1.0e4, dens, temp)
+
+
+# --------------------------------------------------------------------------- #
+# clocks during the timed region (B200_PROFILING.md recipe)
+# --------------------------------------------------------------------------- #
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.f = gpu_index, None, None
+
+    def start(self):
+        try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, reasons = [], set()
+        for line in self.f:
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                out["sm_max_mhz"] = float(p[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            sm.sort()
+            # median of the upper half = under load (idle samples before/after pull the median down)
+            top = sm[len(sm) // 2:]
+            out["sm_mhz"] = top[len(top) // 2]
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# --------------------------------------------------------------------------- #
+# CPU baseline: the oracle port timed on the host
+# --------------------------------------------------------------------------- #
+def _cpu_worker(args):
+    n, seed = args
+    from oracle import cg_oracle as O
+
+    om = _cpu_worker.model
+    t0 = time.perf_counter()
+    om.dm_virial.generate_particles(n, prng=seed)          # mode A sequential C loop + numpy
+    O.generate_gas_particles(om, n, prng=seed + 1)
+    return time.perf_counter() - t0
+
+
+_ORACLE_MODEL = None
+
+
+def cpu_baseline(n_sample, cores):
+    """Oracle port of the reference CPU path: `cores` independent processes, each
+    generating n_sample DM + n_sample gas particles.  Returns (particles/s, seconds)."""
+    global _ORACLE_MODEL
+    if _ORACLE_MODEL is None:
+        _ORACLE_MODEL = build_oracle_model()
+        _ORACLE_MODEL.dm_virial  # tables and f(E) outside the timed region, like the GPU arm
+    _cpu_worker.model = _ORACLE_MODEL
+    if cores == 1:
+        t0 = time.perf_counter()
+        _cpu_worker((n_sample, 25))
+        dt = time.perf_counter() - t0
+    else:
+        import multiprocessing as mp
+
+        ctx = mp.get_context("fork")
+        with ctx.Pool(cores) as pool:
+            pool.map(_cpu_worker, [(1000, 1)] * cores)  # warm the workers
+            t0 = time.perf_counter()
+            pool.map(_cpu_worker, [(n_sample, 25 + 2 * i) for i in range(cores)])
+            dt = time.perf_counter() - t0
+    return 2.0 * n_sample * cores / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    n_sample = 100_000
+    vals = []
+    if args.warmup > 0:
+        cpu_baseline(20_000, cores)
+    t_all = 0.0
+    for _ in range(args.steps):
+        v, dt = cpu_baseline(n_sample, cores)
+        vals.append(v)
+        t_all += dt
+    value = sum(vals) / len(vals)
+    sample = f"{cores} processes x ({n_sample} DM + {n_sample} gas) particles per step, oracle mode A"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------- #
+# CUDA arm
+# --------------------------------------------------------------------------- #
+def run_cuda(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from cluster_generator_b200 import _native as N
+    from cluster_generator_b200.virial import SamplerTables
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L = N.lib()
+    stream = torch.cuda.current_stream()
+
+    # ---- tables (outside the timed region): host quad loops + device f(E) build ----
+    pm = build_product_model()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pm.dm_virial  # first build (includes lazy module/kernel loading)
+    fe_ms = []
+    for _ in range(3):
+        ev0.record()
+        pm.dm_virial._generate_df()
+        ev1.record()
+        torch.cuda.synchronize()
+        fe_ms.append(ev0.elapsed_time(ev1))
+    dm_tabs = pm.dm_virial.sampler_tables()
+    gas_tabs = pm._gas_sampler_tables(None, False)
+
+    n_glob = N_PER_GPU * world
+    lo, hi = rank * N_PER_GPU, (rank + 1) * N_PER_GPU
+    n = hi - lo
+    f64 = torch.float64
+    dm_pos, dm_vel = torch.empty((3, n), dtype=f64, device=dev), torch.empty((3, n), dtype=f64, device=dev)
+    dm_mass = torch.empty(n, dtype=f64, device=dev)
+    g_pos, g_vel = torch.empty((3, n), dtype=f64, device=dev), torch.empty((3, n), dtype=f64, device=dev)
+    g_mass, g_e, g_rho = (torch.empty(n, dtype=f64, device=dev) for _ in range(3))
+    moments = torch.zeros(N.CGB_NMOMENTS, dtype=f64, device=dev)
+
+    def dm_args(seed):
+        a = N.SampleArgs()
+        a.d_workspace = dm_tabs.workspace.data_ptr()
+        a.id_begin, a.id_end, a.ld = lo, hi, n
+        a.particle_mass = dm_tabs.mtot / n_glob
+        a.seed, a.out_dtype = seed, N.CGB_DTYPE_F64
+        a.d_pos, a.d_vel, a.d_mass = dm_pos.data_ptr(), dm_vel.data_ptr(), dm_mass.data_ptr()
+        a.d_moments = moments.data_ptr()
+        return a
+
+    def gas_args(seed):
+        a = N.SampleArgs()
+        a.d_workspace = gas_tabs.workspace.data_ptr()
+        a.id_begin, a.id_end, a.ld = lo, hi, n
+        a.particle_mass = gas_tabs.mtot / n_glob
+        a.seed, a.out_dtype = seed, N.CGB_DTYPE_F64
+        a.d_pos, a.d_vel, a.d_mass = g_pos.data_ptr(), g_vel.data_ptr(), g_mass.data_ptr()
+        return a
+
+    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+
+    def step(i, timed_idx=None):
+        moments.zero_()
+        dm_tabs.tile_counter.zero_()
+        a, g = dm_args(1000 + i), gas_args(5000 + i)
+        sp = N.stream_ptr()
+        if timed_idx is not None:
+            k_ev[timed_idx][0].record()
+        N.check(L.cgb_sample_particles(N.ctypes.byref(a), N.ptr(dm_tabs.tile_counter), sp))
+        if timed_idx is not None:
+            k_ev[timed_idx][1].record()
+        N.check(L.cgb_sample_gas(N.ctypes.byref(g), N.ptr(g_e), N.ptr(g_rho), sp))
+        if world > 1:
+            dist.all_reduce(moments)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.15)
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(args.steps):
+        step(args.warmup + i, i)
+    t1.record()
+    barrier()
+    ms = t0.elapsed_time(t1)
+    clk = clocks.stop() if rank == 0 else None
+    k_ms = sum(a.elapsed_time(b) for a, b in k_ev) / args.steps
+    mom = moments.cpu().numpy()  # last step (all-reduced when world > 1)
+    tt = torch.tensor([ms, k_ms], dtype=f64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms, k_ms = float(tt[0]), float(tt[1])
+    ms_per_step = ms / args.steps
+    value = 2.0 * n_glob / (ms_per_step * 1e-3)
+    tbar = mom[1] / max(mom[0] - mom[13], 1.0)
+
+    # ---- e2e: public API with host tables in, host particles out (rank-local shard) ----
+    import cluster_generator_b200.virial as V
+
+    pin = {}
+
+    def to_host(name, t):
+        if name not in pin:
+            pin[name] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        pin[name].copy_(t, non_blocking=True)
+        return t.numel() * t.element_size()
+
+    def e2e_step(i):
+        # host -> device: the radial tables (rebuilt from the host arrays every step)
+        pm.dm_virial._tables.clear()
+        pm._gas_tables.clear()
+        h2d = 8 * (12 * pm.num_elements + 4)  # CDF + spline-fit inputs of both species
+        p = pm.generate_dm_particles(n_glob, prng=i, shard=(rank, world), diagnostics=False)
+        q = pm.generate_gas_particles(n_glob, prng=i + 1, shard=(rank, world))
+        d2h = 0
+        for k, t in list(p.fields.items()) + list(q.fields.items()):
+            d2h += to_host(k, t.T.contiguous() if t.dim() == 2 and not t.is_contiguous() else t)
+        torch.cuda.synchronize()
+        return h2d, d2h
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_step(0)
+    barrier()
+    w0 = time.perf_counter()
+    for i in range(e2e_steps):
+        h2d, d2h = e2e_step(1 + i)
+    barrier()
+    e2e_s = (time.perf_counter() - w0) / e2e_steps
+    te = torch.tensor([e2e_s], dtype=f64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = 2.0 * n_glob / float(te[0])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (cgb_sample_kernel) ----
+    dfma = N.ctypes.c_double()
+    ffma = N.ctypes.c_double()
+    N.check(L.cgb_measure_dfma_tflops(4096, N.ctypes.byref(dfma), N.stream_ptr()))
+    N.check(L.cgb_measure_ffma_tflops(4096, N.ctypes.byref(ffma), N.stream_ptr()))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    flops_per_particle = F_FIXED + F_TRIAL * tbar
+    k_s = k_ms * 1e-3
+    ach_tflops = n * flops_per_particle / k_s / 1e12
+    ach_gbs = n * B_DM / k_s / 1e9
+    t_pipe = n * flops_per_particle / (dfma.value * 1e12)
+    t_hbm = n * B_DM / (hbm_peak * 1e9)
+    roofline = {
+        "kernel": "cgb_sample_kernel<double,0,false>",
+        "bound": "fp64_pipe" if t_pipe >= t_hbm else "hbm",
+        "achieved": ach_tflops, "peak": dfma.value, "unit": "TFLOP/s", "frac": ach_tflops / dfma.value,
+        "traffic": None,
+        "peak_source": "DFMA microbenchmark measured live (cgb_measure_dfma_tflops); MEASURED_PEAKS.json has no FP64 figure",
+        "algorithmic_flops_per_particle": flops_per_particle, "mean_trials": tbar,
+        "kernel_ms": k_ms, "dm_particles_per_s_kernel": n / k_s,
+        "ffma_peak_tflops": ffma.value, "frac_of_fp32_pipe": ach_tflops / ffma.value,
+        "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+        "exact_fp64_evaluations_per_trial": mom[15] / max(mom[1], 1.0),
+    }
+
+    # ---- CPU baseline (bounded sample, 1 core: the reference is single-threaded) ----
+    n_cpu = 2_000_000
+    cpu_v, cpu_dt = cpu_baseline(n_cpu, 1)
+    t0c = time.perf_counter()
+    from oracle import cg_oracle as O
+    O.VirialEquilibrium(_ORACLE_MODEL, "dark_matter")
+    fe_cpu_s = time.perf_counter() - t0c
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "dm_per_gpu": n, "gas_per_gpu": n, "num_points": pm.num_elements,
+                   "rng": "Philox4x32-10 device", "l2": "outputs 1.28 GB/step/GPU exceed the 126 MB L2",
+                   "parallelism": f"index-sharded x{world}"},
+        "fE_build_ms": min(fe_ms), "fE_build_cpu_ms": 1e3 * fe_cpu_s,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "what": "ClusterModel.generate_dm_particles + generate_gas_particles from host tables, all fields copied to pinned host memory"},
+        "gpu_launches": 2 * args.steps,
+        "roofline": roofline,
+        "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"{n_cpu} DM + {n_cpu} gas particles, oracle mode A C loop + numpy, {cpu_dt:.1f} s",
+                         "host_cores_available": os.cpu_count()},
+        "clocks": clk,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_cuda(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

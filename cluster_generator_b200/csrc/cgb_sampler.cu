@@ -33,8 +33,8 @@
 
 #define NB 4096            // screen buckets
 #define WARPS 16           // warps per CTA
-#define TILE 256           // particles per warp tile
-#define LANE_CAP_PAIRS 96  // trial pairs in lane mode before the warp takes over
+#define TILE 128           // particles per warp tile buffer (two buffers per warp)
+#define NBC 1024           // buckets of the CDF start-index table
 #define SCREEN_REL 4.0e-6  // relative widening of the screen bounds (covers fp32 rounding)
 #define SCREEN_EDGE 0.02   // bucket range widening, in bucket widths
 
@@ -47,6 +47,8 @@ struct SamplerHeader {
     long long off_psi_brk, off_psi_pp;
     long long off_f_brk, off_f_pp;
     long long off_screen;
+    long long off_cdf_lut;  // unsigned[NBC]: lo | hi << 16 search range per u bucket
+    long long off_cdf_iv;   // int2[n_cdf]: starting psi / f piece for CDF interval j
     long long off_aux_brk[2], off_aux_pp[2];
     long long total;
     // scalars computed on the device by the prepare kernels
@@ -66,6 +68,7 @@ static SamplerHeader make_layout(const cgb_sampler_desc* d)
     auto take = [&](long long n) { long long r = o; o += (n + 31) / 32 * 32; return r; };
     h.off_cdf_P = take(h.n_cdf); h.off_cdf_r = take(h.n_cdf); h.off_cdf_s = take(h.n_cdf);
     h.off_psi_brk = take(h.n_psi - 2); h.off_psi_pp = take(4LL * (h.n_psi - 3));
+    h.off_cdf_lut = take(NBC / 2); h.off_cdf_iv = take(h.n_cdf);
     if (h.n_f) {
         h.off_f_brk = take(h.n_f - 2); h.off_f_pp = take(4LL * (h.n_f - 3));
         h.off_screen = take(NB);  // float2 per bucket = one double slot
@@ -107,9 +110,61 @@ __device__ __forceinline__ double pp_eval(const double* __restrict__ brk,
     return pp_eval_at(brk, pp, pp_find(brk, nint, x), x);
 }
 
+// start at piece j0 and walk to the piece that holds x (same rule as pp_find)
+__device__ __forceinline__ int pp_walk(const double* __restrict__ brk, int nint, int j0, double x)
+{
+    int j = min(max(j0, 0), nint - 1);
+    while (j > 0 && x < __ldg(brk + j)) --j;
+    while (j < nint - 1 && x >= __ldg(brk + j + 1)) ++j;
+    return j;
+}
+
+// monotone bucket of a uniform in [0,1); the SAME function builds the table, so the
+// search range it yields always contains the answer
+__device__ __forceinline__ int cdf_bucket(double u)
+{
+    return min(max(__double2int_rd(__dmul_rn(u, (double)NBC)), 0), NBC - 1);
+}
+
 // ---------------------------------------------------------------------------
 // prepare kernels
 // ---------------------------------------------------------------------------
+// cdf_lut[b] = lo | hi << 16 with lo = #{j >= 1 : bucket(P[j]) < b}, hi = #{j >= 1 :
+// bucket(P[j]) <= b}: the largest j with P[j] <= u lies in [lo, hi] for bucket(u) = b.
+__global__ void prep_cdf_lut_kernel(const double* __restrict__ P, int n, unsigned* __restrict__ lut)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= NBC) return;
+    // P is non-decreasing: count by binary search on the bucket value
+    auto count_lt = [&](int bb) {  // #{j in [1, n-1] : bucket(P[j]) < bb}
+        int lo = 1, hi = n;        // first j in [1,n) with bucket(P[j]) >= bb
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (cdf_bucket(P[mid]) < bb) lo = mid + 1; else hi = mid;
+        }
+        return lo - 1;
+    };
+    const int lo = count_lt(b), hi = min(count_lt(b + 1), n - 2);
+    lut[b] = (unsigned)min(lo, n - 2) | ((unsigned)hi << 16);
+}
+
+// cdf_iv[j] = (psi piece, f piece) that hold the middle of CDF interval j
+__global__ void prep_cdf_iv_kernel(const SamplerHeader* __restrict__ hdr, double* __restrict__ base)
+{
+    const SamplerHeader h = *hdr;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= h.n_cdf) return;
+    const double* rc = base + h.off_cdf_r;
+    const double rm = (j + 1 < h.n_cdf) ? 0.5 * (rc[j] + rc[j + 1]) : rc[j];
+    const int ip = pp_find(base + h.off_psi_brk, h.n_psi - 3, rm);
+    int jf = 0;
+    if (h.n_f) {
+        const double psi = pp_eval_at(base + h.off_psi_brk, base + h.off_psi_pp, ip, rm);
+        jf = pp_find(base + h.off_f_brk, h.n_f - 3, psi);
+    }
+    ((int2*)(base + h.off_cdf_iv))[j] = make_int2(ip, jf);
+}
+
 __global__ void prep_cdf_kernel(const double* __restrict__ P, const double* __restrict__ r, int n,
                                 double* __restrict__ oP, double* __restrict__ oR,
                                 double* __restrict__ oS)
@@ -124,24 +179,37 @@ __global__ void prep_cdf_kernel(const double* __restrict__ P, const double* __re
 
 // e_hi = the largest energy any trial can see: max(f knots' upper end, psi(r) over
 // the reachable radii incl. the extrapolated core r in [0, r_0)), padded.
-__global__ void prep_scalars_kernel(SamplerHeader* __restrict__ hdr, double* __restrict__ base)
+__global__ void __launch_bounds__(256) prep_scalars_kernel(SamplerHeader* __restrict__ hdr,
+                                                           double* __restrict__ base)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    __shared__ double s_e[256], s_f[256];
     const SamplerHeader h = *hdr;
     const double* fb = base + h.off_f_brk;
     const double* fp = base + h.off_f_pp;
     const double* pb = base + h.off_psi_brk;
     const double* pp = base + h.off_psi_pp;
     const int nfi = h.n_f - 3, npi = h.n_psi - 3;
-    double e_hi = fb[nfi];
+    double e_hi = fb[nfi], fmaxabs = 0.0;
     // psi over [0, r_max]: sample knots and the extrapolated core
-    for (int j = 0; j <= npi; ++j) e_hi = fmax(e_hi, pp_eval(pb, pp, npi, pb[j]));
-    for (int k = 0; k <= 64; ++k) e_hi = fmax(e_hi, pp_eval(pb, pp, npi, pb[0] * (double)k / 64.0));
-    e_hi *= 1.0 + 1.0e-6;
+    for (int j = threadIdx.x; j <= npi; j += blockDim.x) e_hi = fmax(e_hi, pp_eval(pb, pp, npi, pb[j]));
+    for (int k = threadIdx.x; k <= 64; k += blockDim.x)
+        e_hi = fmax(e_hi, pp_eval(pb, pp, npi, pb[0] * (double)k / 64.0));
+    for (int j = threadIdx.x; j < nfi; j += blockDim.x) fmaxabs = fmax(fmaxabs, fabs(fp[4 * j]));
+    if (threadIdx.x == 0) fmaxabs = fmax(fmaxabs, fabs(pp_eval(fb, fp, nfi, fb[nfi])));
+    s_e[threadIdx.x] = e_hi;
+    s_f[threadIdx.x] = fmaxabs;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+        if (threadIdx.x < o) {
+            s_e[threadIdx.x] = fmax(s_e[threadIdx.x], s_e[threadIdx.x + o]);
+            s_f[threadIdx.x] = fmax(s_f[threadIdx.x], s_f[threadIdx.x + o]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
+    e_hi = s_e[0] * (1.0 + 1.0e-6);
+    fmaxabs = s_f[0];
     // f scale: bring max |f| near 2^40 so fp32 products stay far from denormals
-    double fmaxabs = 0.0;
-    for (int j = 0; j < nfi; ++j) fmaxabs = fmax(fmaxabs, fabs(fp[4 * j]));
-    fmaxabs = fmax(fmaxabs, fabs(pp_eval(fb, fp, nfi, fb[nfi])));
     int ex = 0;
     if (fmaxabs > 0.0 && isfinite(fmaxabs)) frexp(fmaxabs, &ex);
     hdr->e_hi = e_hi;
@@ -236,10 +304,24 @@ struct Tables {
     const double *cdf_P, *cdf_r, *cdf_s;
     const double *psi_brk, *psi_pp;
     const double *f_brk, *f_pp;
+    const unsigned* cdf_lut;
+    const int2* cdf_iv;
     int n_cdf, n_psi_int, n_f_int;
     float inv_w_f;
     double f_scale;
 };
+
+// largest j in [0, n_cdf-2] with P[j] <= u       (np.interp's interval, utils.py:165)
+__device__ __forceinline__ int cdf_find(const Tables& T, double u)
+{
+    const unsigned lh = __ldg(T.cdf_lut + cdf_bucket(u));
+    int lo = (int)(lh & 0xffffu), hi = (int)(lh >> 16);
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(T.cdf_P + mid) <= u) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
 
 // exact accept test, the oracle's operation order (oracle/cg_oracle_c.c: trial()):
 //   v = u1*vesc; v2 = v*v; e = psi - 0.5*v2; accept iff !(f(e)*v2 < u2*fv2esc)
@@ -309,23 +391,40 @@ __device__ __forceinline__ void store_out(void* p, long long i, double v)
 }
 
 // MODE 0: fused DM/star sampler.  MODE 1: velocity-only (Cython seam mirror).
+//
+// Each warp keeps TWO tile buffers in shared memory (rolling window).  Lanes claim
+// particles from the current buffer; when it runs dry the warp sets up the next tile
+// in the other buffer and lanes keep refilling from there while stragglers of the
+// previous tile finish in their lanes.  A tile is written out (phase 2) as soon as
+// all its particles are done.  Only when a buffer must be recycled while it still
+// holds stragglers (rare: the long tail of the trial-count distribution), and at the
+// very end of the kernel, does the whole warp finish a particle cooperatively
+// (64 trials per step; the first accepted trial in sequence order wins, so the
+// result is independent of scheduling).
 template <typename OutT, int MODE, bool HOST_U>
 __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(SampleParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     float2* s_screen = (float2*)smem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* s_psi = (double*)(smem + NB * sizeof(float2)) + (size_t)warp * 4 * TILE;
-    double* s_ves = s_psi + TILE;  // vesc, overwritten by the accepted speed
-    double* s_env = s_ves + TILE;
-    double* s_rad = s_env + TILE;  // radius (MODE 0); trial count as double bits (both modes)
+    // per-warp slot arrays, 2 buffers x TILE slots each
+    double* s_psi = (double*)(smem + NB * sizeof(float2)) + (size_t)warp * 4 * (2 * TILE);
+    double* s_ves = s_psi + 2 * TILE;  // vesc, overwritten by the accepted speed
+    double* s_env = s_ves + 2 * TILE;  // envelope; its low word holds the trial count once done
+    double* s_rad = s_env + 2 * TILE;  // radius (MODE 0)
+    int* s_tri = (int*)s_env;
+    double* s_mom = (double*)(smem + NB * sizeof(float2)) + (size_t)WARPS * 4 * (2 * TILE) +
+                    (size_t)warp * CGB_NMOMENTS;
     const unsigned FULL = 0xffffffffu;
+    const unsigned lt_mask = (1u << lane) - 1u;
 
     const SamplerHeader* hdr = (const SamplerHeader*)p.base;
     Tables T;
     T.cdf_P = p.base + hdr->off_cdf_P; T.cdf_r = p.base + hdr->off_cdf_r; T.cdf_s = p.base + hdr->off_cdf_s;
     T.psi_brk = p.base + hdr->off_psi_brk; T.psi_pp = p.base + hdr->off_psi_pp;
     T.f_brk = p.base + hdr->off_f_brk; T.f_pp = p.base + hdr->off_f_pp;
+    T.cdf_lut = (const unsigned*)(p.base + hdr->off_cdf_lut);
+    T.cdf_iv = (const int2*)(p.base + hdr->off_cdf_iv);
     T.n_cdf = hdr->n_cdf; T.n_psi_int = hdr->n_psi - 3; T.n_f_int = hdr->n_f - 3;
     T.inv_w_f = (float)hdr->inv_w;
     T.f_scale = hdr->f_scale;
@@ -333,27 +432,36 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(SampleParams 
         const float2* g = (const float2*)(p.base + hdr->off_screen);
         for (int i = threadIdx.x; i < NB; i += blockDim.x) s_screen[i] = g[i];
     }
+    if (lane < CGB_NMOMENTS) s_mom[lane] = 0.0;
     __syncthreads();
 
-    // per-lane moment accumulators (reduced once at the end)
-    double m_v2 = 0.0, m_psi = 0.0, m_r = 0.0, m_px = 0.0, m_py = 0.0, m_pz = 0.0, m_vx = 0.0,
-           m_vy = 0.0, m_vz = 0.0;
-    unsigned long long m_trials = 0, m_n = 0, m_nonpos = 0, m_coop = 0, m_fail = 0, m_exact = 0;
-    unsigned m_tmax = 0;
+    unsigned long long m_exact = 0;  // per-lane exact-evaluation counter
+    unsigned m_coop = 0;             // warp-uniform
 
     const long long n_local = p.id_end - p.id_begin;
-    for (;;) {
+    // warp-uniform buffer state
+    // (scalars selected by ternaries: dynamically indexed arrays would go to local memory)
+    long long b_loc0_0 = 0, b_loc0_1 = 0;
+    int b_cnt_0 = 0, b_cnt_1 = 0, b_next_0 = 0, b_next_1 = 0, b_fin_0 = 0, b_fin_1 = 0;
+    bool b_live_0 = false, b_live_1 = false;
+#define BGET(name, b) ((b) ? name##_1 : name##_0)
+#define BSET(name, b, v) do { if (b) name##_1 = (v); else name##_0 = (v); } while (0)
+    bool more_tiles = true;
+    int cur = 0;
+
+    // ---- phase 0: radius, psi, envelope for a freshly claimed tile into buffer b ----
+    auto acquire = [&](int b) -> bool {
         long long tile = 0;
         if (lane == 0) tile = atomicAdd((unsigned long long*)p.tile_counter, 1ULL);
         tile = __shfl_sync(FULL, tile, 0);
-        const long long loc0 = tile * TILE;  // local index of the tile's first particle
-        if (loc0 >= n_local) break;
+        const long long loc0 = tile * TILE;
+        if (loc0 >= n_local) { more_tiles = false; return false; }
         const int cnt = (int)min((long long)TILE, n_local - loc0);
         const long long id0 = (MODE == 0 ? p.id_begin : p.first_id) + loc0;
-
-        // ---------------- phase 0: radius, psi, envelope ----------------
+        int nonpos = 0;
         for (int i = lane; i < cnt; i += 32) {
             double psi, vesc, env;
+            const int s = b * TILE + i;
             if (MODE == 0) {
                 const unsigned long long id = (unsigned long long)(id0 + i);
                 double u;
@@ -364,190 +472,56 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(SampleParams 
                     u = u52(w.x, w.y);
                 }
                 // np.interp(u, P_r, r): j = searchsorted(P_r, u, 'right') - 1        (utils.py:165)
-                int lo = 0, hi = T.n_cdf - 1;
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (__ldg(T.cdf_P + mid) <= u) lo = mid; else hi = mid;
-                }
+                const int j = cdf_find(T, u);
                 const double r = __dadd_rn(
-                    __dmul_rn(__ldg(T.cdf_s + lo), __dsub_rn(u, __ldg(T.cdf_P + lo))),
-                    __ldg(T.cdf_r + lo));
+                    __dmul_rn(__ldg(T.cdf_s + j), __dsub_rn(u, __ldg(T.cdf_P + j))), __ldg(T.cdf_r + j));
                 // psi = energy_spline(r); vesc = 2 psi; fv2esc = vesc * f(psi); vesc = sqrt(vesc)
                 //                                                           (virial.py:191-194)
-                psi = pp_eval(T.psi_brk, T.psi_pp, T.n_psi_int, r);
+                const int2 iv = __ldg(T.cdf_iv + j);
+                psi = pp_eval_at(T.psi_brk, T.psi_pp, pp_walk(T.psi_brk, T.n_psi_int, iv.x, r), r);
                 const double ve2 = __dmul_rn(2.0, psi);
-                env = __dmul_rn(ve2, pp_eval(T.f_brk, T.f_pp, T.n_f_int, psi));
+                env = __dmul_rn(ve2, pp_eval_at(T.f_brk, T.f_pp, pp_walk(T.f_brk, T.n_f_int, iv.y, psi), psi));
                 vesc = sqrt(ve2);
-                s_rad[i] = r;
+                s_rad[s] = r;
             } else {
                 psi = p.in_psi[loc0 + i];
                 vesc = p.in_vesc[loc0 + i];
                 env = p.in_env[loc0 + i];
             }
-            s_psi[i] = psi; s_ves[i] = vesc; s_env[i] = env;
-            if (!(env > 0.0)) ++m_nonpos;
+            s_psi[s] = psi; s_ves[s] = vesc; s_env[s] = env;
+            if (!(env > 0.0)) ++nonpos;
         }
+        nonpos = __reduce_add_sync(FULL, nonpos);
+        if (lane == 0 && nonpos) s_mom[11] += (double)nonpos;
         __syncwarp();
+        BSET(b_loc0, b, loc0); BSET(b_cnt, b, cnt); BSET(b_next, b, 0); BSET(b_fin, b, 0); BSET(b_live, b, true);
+        return true;
+    };
 
-        // ---------------- phase 1: rejection loop ----------------
-        int* s_tri = (int*)(s_env);  // trial counts reuse the env slot once a particle is done
-        int idx = (lane < cnt) ? lane : -1;
-        int next = 32;
-        unsigned pair = 0;
-        float ps = 0.f, vs = 0.f, es = 0.f;
-        auto load_lane = [&](int j) {
-            const double psi = s_psi[j], vesc = s_ves[j], env = s_env[j];
-            ps = (float)psi;
-            vs = (float)(vesc * 0x1.0p-32);
-            es = (float)(env * T.f_scale * 0x1.0p-32);
-            // particles the fp32 screen cannot represent safely -> NaN disables it
-            const float v2max = (float)(vesc * vesc);
-            if (!(v2max > 1.0e-12f && v2max < 1.0e12f) || !(fabsf(es) > 1.0e-30f) || !(psi > 0.0))
-                es = __int_as_float(0x7fc00000);
-            pair = 0;
-        };
-        if (idx >= 0) load_lane(idx);
-
-        // finish particle j cooperatively starting at pair index pair0 (warp-uniform args)
-        auto coop_finish = [&](int j, unsigned pair0) {
-            const double psi = s_psi[j], vesc = s_ves[j], env = s_env[j];
-            float cps = (float)psi, cvs = (float)(vesc * 0x1.0p-32),
-                  ces = (float)(env * T.f_scale * 0x1.0p-32);
-            const float v2max = (float)(vesc * vesc);
-            if (!(v2max > 1.0e-12f && v2max < 1.0e12f) || !(fabsf(ces) > 1.0e-30f) || !(psi > 0.0))
-                ces = __int_as_float(0x7fc00000);
-            const unsigned long long id = (unsigned long long)(id0 + j);
-            unsigned long long pr = pair0;
-            for (;;) {
-                const unsigned long long mine = pr + lane;
-                PairResult r;
-                r.acc = 0; r.n_exact = 0;
-                Philox4 w;
-                w.x = w.y = w.z = w.w = 0;
-                if (mine <= 0xFFFFFFFFull) {
-                    w = philox4x32_10((unsigned)id, (unsigned)(id >> 32), (unsigned)mine,
-                                      CGB_STREAM_VEL_TRIAL, p.seed_lo, p.seed_hi);
-                    r = eval_pair(T, s_screen, w, cps, cvs, ces, psi, vesc, env);
-                }
-                m_exact += r.n_exact;
-                const unsigned hit = __ballot_sync(FULL, r.acc != 0);
-                if (hit) {
-                    const int src = __ffs(hit) - 1;
-                    if (lane == src) {
-                        const unsigned wa = (r.acc == 1) ? w.x : w.z;
-                        const double v = __dmul_rn(u32_to_double(wa) * 0x1.0p-32, vesc);
-                        s_ves[j] = sqrt(__dmul_rn(v, v));
-                        const unsigned long long nt = 2ULL * mine + (unsigned)r.acc;
-                        s_tri[2 * j] = (int)min(nt, 0x7fffffffULL);
-                    }
-                    break;
-                }
-                pr += 32;
-                if (pr > 0xFFFFFFFFull) {  // trial cap reached: report failure
-                    if (lane == 0) { s_ves[j] = __longlong_as_double(0x7ff8000000000000LL); s_tri[2 * j] = -1; }
-                    break;
-                }
-            }
-            __syncwarp();
-        };
-
-        if (HOST_U && p.hu.d_u_trial) {
-            // literal host-supplied (u1,u2)[t_cap] per particle: exact path only
-            for (int i = lane; i < cnt; i += 32) {
-                const double psi = s_psi[i], vesc = s_ves[i], env = s_env[i];
-                const double* uu = p.hu.d_u_trial + (size_t)(loc0 + i) * (size_t)p.hu.t_cap * 2;
-                int acc = -1;
-                double v2 = 0.0;
-                for (long long t = 0; t < p.hu.t_cap; ++t) {
-                    if (exact_accept(T, uu[2 * t], uu[2 * t + 1], psi, vesc, env, v2)) { acc = (int)(t + 1); break; }
-                }
-                s_ves[i] = (acc > 0) ? sqrt(v2) : __longlong_as_double(0x7ff8000000000000LL);
-                s_tri[2 * i] = acc;
-            }
-            __syncwarp();
-        } else {
-            for (;;) {
-                const unsigned act = __ballot_sync(FULL, idx >= 0);
-                if (act == 0) break;
-                if (next >= cnt) {
-                    // tile exhausted: drain the remaining particles cooperatively
-                    unsigned rem = act;
-                    while (rem) {
-                        const int src = __ffs(rem) - 1;
-                        rem &= rem - 1;
-                        const int j = __shfl_sync(FULL, idx, src);
-                        const unsigned p0 = __shfl_sync(FULL, pair, src);
-                        coop_finish(j, p0);
-                        ++m_coop;
-                    }
-                    break;
-                }
-                bool done = false, hard = false;
-                if (idx >= 0) {
-                    const unsigned long long id = (unsigned long long)(id0 + idx);
-                    const Philox4 w = philox4x32_10((unsigned)id, (unsigned)(id >> 32), pair,
-                                                    CGB_STREAM_VEL_TRIAL, p.seed_lo, p.seed_hi);
-                    int sa = screen_trial(s_screen, T.inv_w_f, w.x, w.y, ps, vs, es);
-                    int sb = screen_trial(s_screen, T.inv_w_f, w.z, w.w, ps, vs, es);
-                    if (sa == 2 || (sa == 0 && sb == 2)) {
-                        const PairResult r = eval_pair(T, s_screen, w, ps, vs, es, s_psi[idx],
-                                                       s_ves[idx], s_env[idx]);
-                        m_exact += r.n_exact;
-                        sa = (r.acc == 1); sb = (r.acc == 2);
-                    }
-                    if (sa == 1 || sb == 1) {
-                        const unsigned wa = (sa == 1) ? w.x : w.z;
-                        const double vesc = s_ves[idx];
-                        const double v = __dmul_rn(u32_to_double(wa) * 0x1.0p-32, vesc);
-                        s_ves[idx] = sqrt(__dmul_rn(v, v));
-                        s_tri[2 * idx] = (int)(2u * pair + (sa == 1 ? 1u : 2u));
-                        done = true;
-                    } else {
-                        ++pair;
-                        hard = pair >= LANE_CAP_PAIRS;
-                    }
-                }
-                // long-running particles: the whole warp takes over
-                unsigned hm = __ballot_sync(FULL, hard);
-                while (hm) {
-                    const int src = __ffs(hm) - 1;
-                    hm &= hm - 1;
-                    const int j = __shfl_sync(FULL, idx, src);
-                    const unsigned p0 = __shfl_sync(FULL, pair, src);
-                    coop_finish(j, p0);
-                    ++m_coop;
-                    if (lane == src) done = true;
-                }
-                // refill finished lanes from the tile
-                const unsigned need = __ballot_sync(FULL, done);
-                if (need) {
-                    if (done) {
-                        const int j = next + __popc(need & ((1u << lane) - 1u));
-                        idx = (j < cnt) ? j : -1;
-                        if (idx >= 0) load_lane(idx);
-                    }
-                    next += __popc(need);
-                }
-            }
-            __syncwarp();
-        }
-
-        // ---------------- phase 2: directions and stores ----------------
+    // ---- phase 2: directions and stores for the finished tile in buffer b ----
+    auto epilogue = [&](int b) {
+        const long long loc0 = BGET(b_loc0, b);
+        const int cnt = BGET(b_cnt, b);
+        const long long id0 = (MODE == 0 ? p.id_begin : p.first_id) + loc0;
+        double a_v2 = 0.0, a_psi = 0.0, a_r = 0.0, a_px = 0.0, a_py = 0.0, a_pz = 0.0, a_vx = 0.0,
+               a_vy = 0.0, a_vz = 0.0;
+        unsigned a_tr = 0, a_tmax = 0, a_fail = 0;
+        __syncwarp();
         for (int i = lane; i < cnt; i += 32) {
+            const int s = b * TILE + i;
             const long long loc = loc0 + i;
-            const double psi = s_psi[i];
-            const double v = s_ves[i];
-            const int nt = s_tri[2 * i];
-            ++m_n;
-            if (nt > 0) { m_trials += (unsigned)nt; m_tmax = max(m_tmax, (unsigned)nt); }
-            else ++m_fail;
+            const double psi = s_psi[s];
+            const double v = s_ves[s];
+            const int nt = s_tri[2 * s];
+            if (nt > 0) { a_tr += (unsigned)nt; a_tmax = max(a_tmax, (unsigned)nt); }
+            else ++a_fail;
             if (MODE == 1) {
                 p.speed[loc] = v;
                 if (p.trials) p.trials[loc] = nt;
                 continue;
             }
             const unsigned long long id = (unsigned long long)(id0 + i);
-            const double r = s_rad[i];
+            const double r = s_rad[s];
             double uc, up, ucv, upv;
             if (HOST_U && p.hu.d_u_ct) { uc = p.hu.d_u_ct[loc]; up = p.hu.d_u_ph[loc]; }
             else {
@@ -586,44 +560,225 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(SampleParams 
             if (p.speed) p.speed[loc] = v;
             if (p.trials) p.trials[loc] = nt;
             if (nt > 0) {
-                m_v2 += v * v; m_psi += psi; m_r += r;
-                m_px += px; m_py += py; m_pz += pz; m_vx += vx; m_vy += vy; m_vz += vz;
+                a_v2 += v * v; a_psi += psi; a_r += r;
+                a_px += px; a_py += py; a_pz += pz; a_vx += vx; a_vy += vy; a_vz += vz;
+            }
+        }
+        if (p.moments) {
+            auto wsum = [&](double x) {
+                for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+                return x;
+            };
+            const unsigned tr = __reduce_add_sync(FULL, a_tr);
+            const unsigned tm = __reduce_max_sync(FULL, a_tmax);
+            const unsigned fl = __reduce_add_sync(FULL, a_fail);
+            a_v2 = wsum(a_v2); a_psi = wsum(a_psi); a_r = wsum(a_r);
+            a_px = wsum(a_px); a_py = wsum(a_py); a_pz = wsum(a_pz);
+            a_vx = wsum(a_vx); a_vy = wsum(a_vy); a_vz = wsum(a_vz);
+            if (lane == 0) {
+                s_mom[0] += (double)cnt; s_mom[1] += (double)tr; s_mom[2] = fmax(s_mom[2], (double)tm);
+                s_mom[3] += a_v2; s_mom[4] += a_psi; s_mom[5] += a_px; s_mom[6] += a_py; s_mom[7] += a_pz;
+                s_mom[8] += a_vx; s_mom[9] += a_vy; s_mom[10] += a_vz; s_mom[13] += (double)fl;
+                s_mom[14] += a_r;
             }
         }
         __syncwarp();
+        BSET(b_live, b, false);
+    };
+
+    // ---- per-lane trial state ----
+    int slot = -1;
+    unsigned pair = 0;
+    float ps = 0.f, vs = 0.f, es = 0.f;
+    auto lane_floats = [&](double psi, double vesc, double env, float& fps, float& fvs, float& fes) {
+        fps = (float)psi;
+        fvs = (float)(vesc * 0x1.0p-32);
+        fes = (float)(env * T.f_scale * 0x1.0p-32);
+        // particles the fp32 screen cannot represent safely: NaN makes every screen
+        // comparison false, so they always take the exact path
+        const float v2max = (float)(vesc * vesc);
+        if (!(v2max > 1.0e-12f && v2max < 1.0e12f) || !(fabsf(fes) > 1.0e-30f) || !(psi > 0.0))
+            fes = __int_as_float(0x7fc00000);
+    };
+
+    // finish the particle in slot s cooperatively from pair index pair0 (warp-uniform args)
+    auto coop_finish = [&](int s, unsigned pair0) {
+        const int b = s / TILE;
+        const double psi = s_psi[s], vesc = s_ves[s], env = s_env[s];
+        float cps, cvs, ces;
+        lane_floats(psi, vesc, env, cps, cvs, ces);
+        const unsigned long long id =
+            (unsigned long long)((MODE == 0 ? p.id_begin : p.first_id) + BGET(b_loc0, b) + (s - b * TILE));
+        unsigned long long pr = pair0;
+        __syncwarp();
+        for (;;) {
+            const unsigned long long mine = pr + lane;
+            PairResult r;
+            r.acc = 0; r.n_exact = 0;
+            Philox4 w;
+            w.x = w.y = w.z = w.w = 0;
+            if (mine <= 0xFFFFFFFFull) {
+                w = philox4x32_10((unsigned)id, (unsigned)(id >> 32), (unsigned)mine,
+                                  CGB_STREAM_VEL_TRIAL, p.seed_lo, p.seed_hi);
+                r = eval_pair(T, s_screen, w, cps, cvs, ces, psi, vesc, env);
+            }
+            m_exact += r.n_exact;
+            const unsigned hit = __ballot_sync(FULL, r.acc != 0);
+            if (hit) {
+                const int src = __ffs(hit) - 1;
+                if (lane == src) {
+                    const unsigned wa = (r.acc == 1) ? w.x : w.z;
+                    const double v = __dmul_rn(u32_to_double(wa) * 0x1.0p-32, vesc);
+                    s_ves[s] = sqrt(__dmul_rn(v, v));
+                    const unsigned long long nt = 2ULL * mine + (unsigned)r.acc;
+                    s_tri[2 * s] = (int)min(nt, 0x7fffffffULL);
+                }
+                break;
+            }
+            pr += 32;
+            if (pr > 0xFFFFFFFFull) {  // trial cap reached: report failure
+                if (lane == 0) { s_ves[s] = __longlong_as_double(0x7ff8000000000000LL); s_tri[2 * s] = -1; }
+                break;
+            }
+        }
+        ++m_coop;
+        __syncwarp();
+    };
+
+    // cooperatively finish every in-flight particle that lives in buffer b (b < 0: any)
+    auto finish_stragglers = [&](int b) {
+        unsigned rem = __ballot_sync(FULL, slot >= 0 && (b < 0 || slot / TILE == b));
+        while (rem) {
+            const int src = __ffs(rem) - 1;
+            rem &= rem - 1;
+            const int s = __shfl_sync(FULL, slot, src);
+            const unsigned p0 = __shfl_sync(FULL, pair, src);
+            coop_finish(s, p0);
+            if (s / TILE) ++b_fin_1; else ++b_fin_0;
+            if (lane == src) slot = -1;
+        }
+    };
+
+    if (HOST_U && p.hu.d_u_trial) {
+        // literal host-supplied (u1,u2)[t_cap] per particle: exact path only, tile by tile
+        while (acquire(0)) {
+            for (int i = lane; i < b_cnt_0; i += 32) {
+                const double psi = s_psi[i], vesc = s_ves[i], env = s_env[i];
+                const double* uu = p.hu.d_u_trial + (size_t)(b_loc0_0 + i) * (size_t)p.hu.t_cap * 2;
+                int acc = -1;
+                double v2 = 0.0;
+                for (long long t = 0; t < p.hu.t_cap; ++t) {
+                    if (exact_accept(T, uu[2 * t], uu[2 * t + 1], psi, vesc, env, v2)) { acc = (int)(t + 1); break; }
+                }
+                s_ves[i] = (acc > 0) ? sqrt(v2) : __longlong_as_double(0x7ff8000000000000LL);
+                s_tri[2 * i] = acc;
+            }
+            epilogue(0);
+        }
+    } else if (acquire(0)) {
+        for (;;) {
+            // ---- refill idle lanes from the current buffer, rolling to the next tile ----
+            unsigned need = __ballot_sync(FULL, slot < 0);
+            while (need) {
+                const int avail = BGET(b_cnt, cur) - BGET(b_next, cur);
+                if (avail == 0) {
+                    if (!more_tiles) break;
+                    const int other = cur ^ 1;
+                    if (BGET(b_live, other)) {  // recycle: its stragglers are finished by the whole warp
+                        finish_stragglers(other);
+                        epilogue(other);
+                    }
+                    if (!acquire(other)) break;
+                    cur = other;
+                    need = __ballot_sync(FULL, slot < 0);
+                    continue;
+                }
+                const int want = __popc(need);
+                const int rank = __popc(need & lt_mask);
+                if (((need >> lane) & 1u) && rank < avail) {
+                    slot = cur * TILE + BGET(b_next, cur) + rank;
+                    lane_floats(s_psi[slot], s_ves[slot], s_env[slot], ps, vs, es);
+                    pair = 0;
+                }
+                BSET(b_next, cur, BGET(b_next, cur) + min(want, avail));
+                if (want <= avail) break;
+                need = __ballot_sync(FULL, slot < 0);
+            }
+            const unsigned act = __ballot_sync(FULL, slot >= 0);
+            if (act == 0) break;
+            if (!more_tiles && BGET(b_next, cur) == BGET(b_cnt, cur)) {
+                // nothing left to claim anywhere: final drain
+                finish_stragglers(-1);
+                break;
+            }
+            // ---- one Philox call = two trials for every active lane ----
+            bool done = false;
+            if (slot >= 0) {
+                const int b = slot / TILE;
+                const unsigned long long id = (unsigned long long)(
+                    (MODE == 0 ? p.id_begin : p.first_id) + BGET(b_loc0, b) + (slot - b * TILE));
+                const Philox4 w = philox4x32_10((unsigned)id, (unsigned)(id >> 32), pair,
+                                                CGB_STREAM_VEL_TRIAL, p.seed_lo, p.seed_hi);
+                int sa = screen_trial(s_screen, T.inv_w_f, w.x, w.y, ps, vs, es);
+                int sb = screen_trial(s_screen, T.inv_w_f, w.z, w.w, ps, vs, es);
+                if (sa == 2 || (sa == 0 && sb == 2)) {
+                    const PairResult r = eval_pair(T, s_screen, w, ps, vs, es, s_psi[slot], s_ves[slot],
+                                                   s_env[slot]);
+                    m_exact += r.n_exact;
+                    sa = (r.acc == 1); sb = (r.acc == 2);
+                }
+                if (sa == 1 || sb == 1) {
+                    const unsigned wa = (sa == 1) ? w.x : w.z;
+                    const double vesc = s_ves[slot];
+                    const double v = __dmul_rn(u32_to_double(wa) * 0x1.0p-32, vesc);
+                    s_ves[slot] = sqrt(__dmul_rn(v, v));
+                    s_tri[2 * slot] = (int)(2u * pair + (sa == 1 ? 1u : 2u));
+                    done = true;
+                } else if (++pair == 0u) {  // 2^33 trials exhausted
+                    s_ves[slot] = __longlong_as_double(0x7ff8000000000000LL);
+                    s_tri[2 * slot] = -1;
+                    done = true;
+                }
+            }
+            const unsigned d0 = __ballot_sync(FULL, done && slot < TILE);
+            const unsigned d1 = __ballot_sync(FULL, done && slot >= TILE);
+            if (done) slot = -1;
+            b_fin_0 += __popc(d0);
+            b_fin_1 += __popc(d1);
+            // a fully finished tile that is no longer being claimed from goes out
+            const int other = cur ^ 1;
+            if (BGET(b_live, other) && BGET(b_fin, other) == BGET(b_cnt, other)) epilogue(other);
+        }
+        // write out whatever is still held
+        if (BGET(b_live, cur ^ 1)) epilogue(cur ^ 1);
+        if (BGET(b_live, cur)) epilogue(cur);
     }
 
     // ---------------- moments ----------------
     if (p.moments) {
-        auto wsum = [&](double x) {
-            for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
-            return x;
-        };
-        double vals[CGB_NMOMENTS];
-        vals[0] = (double)m_n; vals[1] = (double)m_trials; vals[2] = 0.0;
-        vals[3] = m_v2; vals[4] = m_psi; vals[5] = m_px; vals[6] = m_py; vals[7] = m_pz;
-        vals[8] = m_vx; vals[9] = m_vy; vals[10] = m_vz; vals[11] = (double)m_nonpos;
-        vals[12] = (double)m_coop / 32.0;  // every lane counted each cooperative finish
-        vals[13] = (double)m_fail; vals[14] = m_r; vals[15] = (double)m_exact;
-        unsigned tmax = m_tmax;
-        for (int o = 16; o; o >>= 1) tmax = max(tmax, __shfl_xor_sync(FULL, tmax, o));
-#pragma unroll
-        for (int k = 0; k < CGB_NMOMENTS; ++k) {
-            if (k == 2) continue;
-            const double s = wsum(vals[k]);
-            if (lane == 0 && s != 0.0) atomicAdd(p.moments + k, s);
-        }
+        unsigned long long ex = m_exact;
+        for (int o = 16; o; o >>= 1) ex += __shfl_xor_sync(FULL, ex, o);
+        __syncwarp();
         if (lane == 0) {
-            // max via CAS on the double's bits (non-negative doubles order like integers)
-            unsigned long long* a = (unsigned long long*)(p.moments + 2);
-            atomicMax(a, (unsigned long long)__double_as_longlong((double)tmax));
+            s_mom[12] = (double)m_coop;
+            s_mom[15] = (double)ex;
+        }
+        __syncwarp();
+        if (lane < CGB_NMOMENTS && lane != 2) {
+            const double v = s_mom[lane];
+            if (v != 0.0) atomicAdd(p.moments + lane, v);
+        }
+        if (lane == 2) {
+            // max via integer atomicMax on the bits (non-negative doubles order like integers)
+            atomicMax((unsigned long long*)(p.moments + 2), (unsigned long long)__double_as_longlong(s_mom[2]));
         }
     }
 }
 
 static size_t sample_smem_bytes()
 {
-    return NB * sizeof(float2) + (size_t)WARPS * 4 * TILE * sizeof(double);
+    return NB * sizeof(float2) + (size_t)WARPS * 4 * (2 * TILE) * sizeof(double) +
+           (size_t)WARPS * CGB_NMOMENTS * sizeof(double);
 }
 
 template <typename OutT, int MODE, bool HOST_U>
@@ -761,7 +916,7 @@ __global__ void cgb_psi_at_kernel(const double* __restrict__ base, const double*
 static int check_desc(const cgb_sampler_desc* d, const char* who)
 {
     CGB_REQUIRE(d != nullptr, "%s: null descriptor", who);
-    CGB_REQUIRE(d->n_cdf >= 2 && d->d_cdf_P && d->d_cdf_r, "%s: CDF table needs >= 2 entries", who);
+    CGB_REQUIRE(d->n_cdf >= 2 && d->n_cdf < 65535 && d->d_cdf_P && d->d_cdf_r, "%s: CDF table needs >= 2 entries", who);
     CGB_REQUIRE(d->n_psi >= 4 && d->d_psi_t && d->d_psi_c, "%s: psi spline needs >= 4 coefficients", who);
     CGB_REQUIRE((d->d_f_t == nullptr) == (d->d_f_c == nullptr), "%s: f knots/coeffs must both be given", who);
     if (d->d_f_t) CGB_REQUIRE(d->n_f >= 4, "%s: f spline needs >= 4 coefficients", who);
@@ -796,6 +951,7 @@ extern "C" int cgb_sampler_prepare(const cgb_sampler_desc* desc, void* d_workspa
     prep_cdf_kernel<<<(h.n_cdf + 255) / 256, 256, 0, s>>>(desc->d_cdf_P, desc->d_cdf_r, h.n_cdf,
                                                          base + h.off_cdf_P, base + h.off_cdf_r,
                                                          base + h.off_cdf_s);
+    prep_cdf_lut_kernel<<<NBC / 256, 256, 0, s>>>(desc->d_cdf_P, h.n_cdf, (unsigned*)(base + h.off_cdf_lut));
     if ((rc = cgb_launch_pp_convert(desc->d_psi_t, desc->d_psi_c, h.n_psi, base + h.off_psi_brk,
                                     base + h.off_psi_pp, s))) return rc;
     for (int k = 0; k < h.n_aux; ++k)
@@ -804,9 +960,10 @@ extern "C" int cgb_sampler_prepare(const cgb_sampler_desc* desc, void* d_workspa
     if (h.n_f) {
         if ((rc = cgb_launch_pp_convert(desc->d_f_t, desc->d_f_c, h.n_f, base + h.off_f_brk,
                                         base + h.off_f_pp, s))) return rc;
-        prep_scalars_kernel<<<1, 32, 0, s>>>((SamplerHeader*)base, base);
+        prep_scalars_kernel<<<1, 256, 0, s>>>((SamplerHeader*)base, base);
         prep_screen_kernel<<<NB / 256, 256, 0, s>>>((const SamplerHeader*)base, base);
     }
+    prep_cdf_iv_kernel<<<(h.n_cdf + 255) / 256, 256, 0, s>>>((const SamplerHeader*)base, base);
     CGB_CUDA_CHECK(cudaGetLastError());
     return CGB_OK;
 }

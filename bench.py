@@ -248,12 +248,11 @@ def run_cuda(args):
 
     def step(i, timed_idx=None):
         moments.zero_()
-        dm_tabs.tile_counter.zero_()
         a, g = dm_args(1000 + i), gas_args(5000 + i)
         sp = N.stream_ptr()
         if timed_idx is not None:
             k_ev[timed_idx][0].record()
-        N.check(L.cgb_sample_particles(N.ctypes.byref(a), N.ptr(dm_tabs.tile_counter), sp))
+        N.check(L.cgb_sample_particles(N.ctypes.byref(a), N.ptr(dm_tabs.scratch), dm_tabs.scratch.numel(), sp))
         if timed_idx is not None:
             k_ev[timed_idx][1].record()
         N.check(L.cgb_sample_gas(N.ctypes.byref(g), N.ptr(g_e), N.ptr(g_rho), sp))

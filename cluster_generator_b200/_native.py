@@ -14,7 +14,7 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_int, c_int32, c_int
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcgb200.so")
+LIB_PATH = os.environ.get("CGB200_LIB") or os.path.join(_HERE, "lib", "libcgb200.so")
 
 CGB_OK = 0
 CGB_E_INVALID = -1
@@ -77,7 +77,8 @@ SYMBOLS = [
                                c_double, c_int, c_void_p, c_void_p]),
     ("cgb_sampler_workspace_bytes", c_size_t, [POINTER(SamplerDesc)]),
     ("cgb_sampler_prepare", c_int, [POINTER(SamplerDesc), c_void_p, c_size_t, c_void_p]),
-    ("cgb_sample_particles", c_int, [POINTER(SampleArgs), c_void_p, c_void_p]),
+    ("cgb_sample_scratch_bytes", c_size_t, []),
+    ("cgb_sample_particles", c_int, [POINTER(SampleArgs), c_void_p, c_size_t, c_void_p]),
     ("cgb_assemble_particles", c_int, [POINTER(SampleArgs), c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     ("cgb_generate_velocities_workspace_bytes", c_size_t, [c_int]),
     ("cgb_generate_velocities", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,

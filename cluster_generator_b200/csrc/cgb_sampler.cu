@@ -32,9 +32,16 @@
 #include "cgb_spline.cuh"
 
 #define NB 4096            // screen buckets
+#ifndef WARPS
 #define WARPS 16           // warps per CTA
+#endif
+#ifndef TILE
 #define TILE 128           // particles per warp tile buffer (two buffers per warp)
+#endif
 #define NBC 1024           // buckets of the CDF start-index table
+#define HARD_PAIRS 32768   // pair index beyond which a particle is deferred to the grid-wide pass
+#define HARD_CAP 4096      // capacity of the deferred-particle list
+#define TRI_DEFERRED (-2147483647)
 #define SCREEN_REL 4.0e-6  // relative widening of the screen bounds (covers fp32 rounding)
 #define SCREEN_EDGE 0.02   // bucket range widening, in bucket widths
 
@@ -80,6 +87,25 @@ static SamplerHeader make_layout(const cgb_sampler_desc* d)
     h.total = o;
     return h;
 }
+
+// per-call scratch (caller-provided, cgb_sample_scratch_bytes()): dynamic tile counter
+// and the list of particles whose trial count is so large that the whole GRID finishes
+// them in a second pass (the trial-count distribution has a ~1e-7 tail of >1e6 trials)
+struct HardEntry {
+    unsigned long long id;         // global particle id (Philox counter)
+    long long loc;                 // local output index
+    double psi, vesc, env;
+    unsigned long long next_pair;  // first pair index not yet examined
+    unsigned long long best;       // smallest accepted trial index found so far (~0: none)
+    unsigned long long pad;
+};
+struct ScratchHeader {
+    unsigned long long tile_counter;
+    unsigned int hard_count;
+    unsigned int done_ctas;
+    unsigned long long pad[6];
+};
+static_assert(sizeof(HardEntry) == 64 && sizeof(ScratchHeader) == 64, "scratch layout");
 
 // ---------------------------------------------------------------------------
 // piecewise-polynomial evaluation (exact path)
@@ -294,7 +320,7 @@ struct SampleParams {
     void* mass; void* pot;
     double* radius; double* speed; int* trials; double* moments;
     cgb_host_uniforms hu;
-    long long* tile_counter;
+    ScratchHeader* scratch;
     // velocity-only mode (cgb_generate_velocities): per-particle inputs
     const double* in_psi; const double* in_vesc; const double* in_env;
     long long first_id;
@@ -437,6 +463,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(SampleParams 
 
     unsigned long long m_exact = 0;  // per-lane exact-evaluation counter
     unsigned m_coop = 0;             // warp-uniform
+    bool no_defer = false;           // warp-uniform: the deferred list overflowed
 
     const long long n_local = p.id_end - p.id_begin;
     // warp-uniform buffer state
@@ -452,7 +479,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(SampleParams 
     // ---- phase 0: radius, psi, envelope for a freshly claimed tile into buffer b ----
     auto acquire = [&](int b) -> bool {
         long long tile = 0;
-        if (lane == 0) tile = atomicAdd((unsigned long long*)p.tile_counter, 1ULL);
+        if (lane == 0) tile = atomicAdd(&p.scratch->tile_counter, 1ULL);
         tile = __shfl_sync(FULL, tile, 0);
         const long long loc0 = tile * TILE;
         if (loc0 >= n_local) { more_tiles = false; return false; }
@@ -513,11 +540,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(SampleParams 
             const double psi = s_psi[s];
             const double v = s_ves[s];
             const int nt = s_tri[2 * s];
+            const bool deferred = nt == TRI_DEFERRED;  // speed comes from cgb_hard_kernel
             if (nt > 0) { a_tr += (unsigned)nt; a_tmax = max(a_tmax, (unsigned)nt); }
-            else ++a_fail;
+            else if (!deferred) ++a_fail;
             if (MODE == 1) {
-                p.speed[loc] = v;
-                if (p.trials) p.trials[loc] = nt;
+                if (!deferred) {
+                    p.speed[loc] = v;
+                    if (p.trials) p.trials[loc] = nt;
+                }
                 continue;
             }
             const unsigned long long id = (unsigned long long)(id0 + i);
@@ -551,18 +581,20 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(SampleParams 
             store_out<OutT>(p.pos, loc, px);
             store_out<OutT>(p.pos, p.ld + loc, py);
             store_out<OutT>(p.pos, 2 * p.ld + loc, pz);
-            store_out<OutT>(p.vel, loc, vx);
-            store_out<OutT>(p.vel, p.ld + loc, vy);
-            store_out<OutT>(p.vel, 2 * p.ld + loc, vz);
+            if (!deferred) {
+                store_out<OutT>(p.vel, loc, vx);
+                store_out<OutT>(p.vel, p.ld + loc, vy);
+                store_out<OutT>(p.vel, 2 * p.ld + loc, vz);
+                if (p.speed) p.speed[loc] = v;
+                if (p.trials) p.trials[loc] = nt;
+            }
             if (p.mass) store_out<OutT>(p.mass, loc, p.particle_mass);
             if (p.pot) store_out<OutT>(p.pot, loc, -psi);
             if (p.radius) p.radius[loc] = r;
-            if (p.speed) p.speed[loc] = v;
-            if (p.trials) p.trials[loc] = nt;
-            if (nt > 0) {
-                a_v2 += v * v; a_psi += psi; a_r += r;
-                a_px += px; a_py += py; a_pz += pz; a_vx += vx; a_vy += vy; a_vz += vz;
+            if (nt > 0 || deferred) {
+                a_psi += psi; a_r += r; a_px += px; a_py += py; a_pz += pz;
             }
+            if (nt > 0) { a_v2 += v * v; a_vx += vx; a_vy += vy; a_vz += vz; }
         }
         if (p.moments) {
             auto wsum = [&](double x) {
@@ -636,6 +668,23 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(SampleParams 
                 break;
             }
             pr += 32;
+            if (pr >= HARD_PAIRS && !no_defer) {
+                // long tail: hand the particle to the grid-wide pass (cgb_hard_kernel)
+                unsigned h = 0;
+                if (lane == 0) h = atomicAdd(&p.scratch->hard_count, 1u);
+                h = __shfl_sync(FULL, h, 0);
+                if (h < HARD_CAP) {
+                    if (lane == 0) {
+                        HardEntry* e = (HardEntry*)(p.scratch + 1) + h;
+                        e->id = id; e->loc = BGET(b_loc0, b) + (s - b * TILE);
+                        e->psi = psi; e->vesc = vesc; e->env = env;
+                        e->next_pair = pr; e->best = ~0ULL;
+                        s_ves[s] = 0.0; s_tri[2 * s] = TRI_DEFERRED;
+                    }
+                    break;
+                }
+                no_defer = true;  // list full: keep going in the warp
+            }
             if (pr > 0xFFFFFFFFull) {  // trial cap reached: report failure
                 if (lane == 0) { s_ves[s] = __longlong_as_double(0x7ff8000000000000LL); s_tri[2 * s] = -1; }
                 break;
@@ -775,6 +824,141 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(SampleParams 
     }
 }
 
+// Grid-wide pass over the deferred particles: CTA c examines trial chunks c, c+G, ...
+// (512 pairs each) until a chunk starts beyond the smallest accepted trial found so far
+// (atomicMin).  The last CTA to finish writes the speeds / velocity vectors.  The
+// result is the first accepted trial in sequence order -- identical to the serial loop.
+template <typename OutT, int MODE, bool HOST_U>
+__global__ void __launch_bounds__(512, 1) cgb_hard_kernel(SampleParams p)
+{
+    ScratchHeader* sh = p.scratch;
+    const unsigned n_hard = min(sh->hard_count, (unsigned)HARD_CAP);
+    if (n_hard == 0) return;
+    extern __shared__ __align__(16) unsigned char smem[];
+    float2* s_screen = (float2*)smem;
+    __shared__ unsigned long long s_best[16];
+    __shared__ unsigned long long s_bcast;
+    __shared__ int s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned FULL = 0xffffffffu;
+    const SamplerHeader* hdr = (const SamplerHeader*)p.base;
+    Tables T;
+    T.cdf_P = p.base + hdr->off_cdf_P; T.cdf_r = p.base + hdr->off_cdf_r; T.cdf_s = p.base + hdr->off_cdf_s;
+    T.psi_brk = p.base + hdr->off_psi_brk; T.psi_pp = p.base + hdr->off_psi_pp;
+    T.f_brk = p.base + hdr->off_f_brk; T.f_pp = p.base + hdr->off_f_pp;
+    T.cdf_lut = (const unsigned*)(p.base + hdr->off_cdf_lut);
+    T.cdf_iv = (const int2*)(p.base + hdr->off_cdf_iv);
+    T.n_cdf = hdr->n_cdf; T.n_psi_int = hdr->n_psi - 3; T.n_f_int = hdr->n_f - 3;
+    T.inv_w_f = (float)hdr->inv_w;
+    T.f_scale = hdr->f_scale;
+    {
+        const float2* g = (const float2*)(p.base + hdr->off_screen);
+        for (int i = threadIdx.x; i < NB; i += blockDim.x) s_screen[i] = g[i];
+    }
+    __syncthreads();
+    HardEntry* ent = (HardEntry*)(sh + 1);
+    for (unsigned h = 0; h < n_hard; ++h) {
+        const HardEntry e = ent[h];
+        float cps = (float)e.psi, cvs = (float)(e.vesc * 0x1.0p-32), ces = (float)(e.env * T.f_scale * 0x1.0p-32);
+        const float v2max = (float)(e.vesc * e.vesc);
+        if (!(v2max > 1.0e-12f && v2max < 1.0e12f) || !(fabsf(ces) > 1.0e-30f) || !(e.psi > 0.0))
+            ces = __int_as_float(0x7fc00000);
+        volatile unsigned long long* bestp = &ent[h].best;
+        for (unsigned long long chunk = blockIdx.x;; chunk += gridDim.x) {
+            const unsigned long long start = e.next_pair + chunk * 512ULL;
+            if (threadIdx.x == 0) s_bcast = *bestp;
+            __syncthreads();
+            const unsigned long long best = s_bcast;
+            if (start > 0xFFFFFFFFull || 2ULL * start >= best) break;
+            const unsigned long long mine = start + threadIdx.x;
+            unsigned long long t = ~0ULL;
+            if (mine <= 0xFFFFFFFFull) {
+                const Philox4 w = philox4x32_10((unsigned)e.id, (unsigned)(e.id >> 32), (unsigned)mine,
+                                                CGB_STREAM_VEL_TRIAL, p.seed_lo, p.seed_hi);
+                const PairResult r = eval_pair(T, s_screen, w, cps, cvs, ces, e.psi, e.vesc, e.env);
+                if (r.acc) t = 2ULL * mine + (unsigned)(r.acc - 1);
+            }
+            for (int o = 16; o; o >>= 1) {
+                const unsigned long long u = __shfl_xor_sync(FULL, t, o);
+                t = u < t ? u : t;
+            }
+            if (lane == 0) s_best[warp] = t;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned long long m = ~0ULL;
+                for (int k = 0; k < 16; ++k) m = s_best[k] < m ? s_best[k] : m;
+                if (m != ~0ULL) atomicMin((unsigned long long*)&ent[h].best, m);
+                s_bcast = m;
+            }
+            __syncthreads();
+            const bool found = s_bcast != ~0ULL;
+            __syncthreads();
+            if (found) break;
+        }
+        __syncthreads();
+    }
+    // last CTA finalises
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&sh->done_ctas, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (unsigned h = threadIdx.x; h < n_hard; h += blockDim.x) {
+        const HardEntry e = ent[h];
+        const unsigned long long best = *(volatile unsigned long long*)&ent[h].best;
+        double v;
+        int nt;
+        if (best == ~0ULL) {
+            v = __longlong_as_double(0x7ff8000000000000LL);
+            nt = -1;
+        } else {
+            const Philox4 w = philox4x32_10((unsigned)e.id, (unsigned)(e.id >> 32), (unsigned)(best >> 1),
+                                            CGB_STREAM_VEL_TRIAL, p.seed_lo, p.seed_hi);
+            const unsigned wa = (best & 1ULL) ? w.z : w.x;
+            const double vv = __dmul_rn(u32_to_double(wa) * 0x1.0p-32, e.vesc);
+            v = sqrt(__dmul_rn(vv, vv));
+            nt = (int)min(best + 1ULL, 0x7fffffffULL);
+        }
+        const long long loc = e.loc;
+        if (MODE == 1) {
+            p.speed[loc] = v;
+            if (p.trials) p.trials[loc] = nt;
+        } else {
+            double ucv, upv;
+            if (HOST_U && p.hu.d_u_ctv) { ucv = p.hu.d_u_ctv[loc]; upv = p.hu.d_u_phv[loc]; }
+            else {
+                const Philox4 w = philox4x32_10((unsigned)e.id, (unsigned)(e.id >> 32), 0u,
+                                                CGB_STREAM_VEL_DIR, p.seed_lo, p.seed_hi);
+                ucv = u52(w.x, w.y); upv = u52(w.z, w.w);
+            }
+            const double ctv = __dadd_rn(-1.0, __dmul_rn(2.0, ucv));
+            const double stv = sqrt(__dmul_rn(__dsub_rn(1.0, ctv), __dadd_rn(1.0, ctv)));
+            double spv, cpv;
+            sincospi(__dmul_rn(2.0, upv), &spv, &cpv);
+            const double vsn = __dmul_rn(v, stv);
+            const double vx = __dmul_rn(vsn, cpv), vy = __dmul_rn(vsn, spv), vz = __dmul_rn(v, ctv);
+            store_out<OutT>(p.vel, loc, vx);
+            store_out<OutT>(p.vel, p.ld + loc, vy);
+            store_out<OutT>(p.vel, 2 * p.ld + loc, vz);
+            if (p.speed) p.speed[loc] = v;
+            if (p.trials) p.trials[loc] = nt;
+            if (p.moments && nt > 0) {
+                atomicAdd(p.moments + 3, v * v);
+                atomicAdd(p.moments + 8, vx); atomicAdd(p.moments + 9, vy); atomicAdd(p.moments + 10, vz);
+            }
+        }
+        if (p.moments) {
+            if (nt > 0) {
+                atomicAdd(p.moments + 1, (double)nt);
+                atomicMax((unsigned long long*)(p.moments + 2), (unsigned long long)__double_as_longlong((double)nt));
+            } else {
+                atomicAdd(p.moments + 13, 1.0);
+            }
+        }
+    }
+}
+
 static size_t sample_smem_bytes()
 {
     return NB * sizeof(float2) + (size_t)WARPS * 4 * (2 * TILE) * sizeof(double) +
@@ -795,7 +979,10 @@ static int launch_sample(const SampleParams& sp, cudaStream_t s)
     long long ctas = (tiles + WARPS - 1) / WARPS;
     if (ctas > sms) ctas = sms;
     if (ctas < 1) ctas = 1;
+    CGB_CUDA_CHECK(cudaMemsetAsync(sp.scratch, 0, sizeof(ScratchHeader), s));
     cgb_sample_kernel<OutT, MODE, HOST_U><<<(unsigned)ctas, WARPS * 32, smem, s>>>(sp);
+    // grid-wide pass over the (rare) deferred particles; exits at once when there are none
+    cgb_hard_kernel<OutT, MODE, HOST_U><<<sms, 512, NB * sizeof(float2), s>>>(sp);
     CGB_CUDA_CHECK(cudaGetLastError());
     return CGB_OK;
 }
@@ -999,14 +1186,24 @@ static bool any_host_u(const cgb_host_uniforms& hu)
     return hu.d_u_r || hu.d_u_ct || hu.d_u_ctv || hu.d_u_trial;
 }
 
-extern "C" int cgb_sample_particles(const cgb_sample_args* args, int64_t* d_tile_counter, void* stream)
+extern "C" size_t cgb_sample_scratch_bytes(void)
+{
+    return sizeof(ScratchHeader) + (size_t)HARD_CAP * sizeof(HardEntry);
+}
+
+extern "C" int cgb_sample_particles(const cgb_sample_args* args, void* d_scratch, size_t scratch_bytes,
+                                    void* stream)
 {
     SampleParams sp;
     int rc = fill_params(args, sp, "cgb_sample_particles", true);
     if (rc) return rc;
-    CGB_REQUIRE(d_tile_counter != nullptr, "cgb_sample_particles: null tile counter");
+    if (d_scratch == nullptr || scratch_bytes < cgb_sample_scratch_bytes() || ((uintptr_t)d_scratch & 63)) {
+        cgb_set_error("cgb_sample_particles: scratch %zu B (need %zu, 64-byte aligned)", scratch_bytes,
+                      cgb_sample_scratch_bytes());
+        return CGB_E_WORKSPACE;
+    }
     if (sp.id_end == sp.id_begin) return CGB_OK;
-    sp.tile_counter = (long long*)d_tile_counter;
+    sp.scratch = (ScratchHeader*)d_scratch;
     cudaStream_t s = (cudaStream_t)stream;
     const bool f32 = args->out_dtype == CGB_DTYPE_F32;
     if (any_host_u(args->hu))
@@ -1081,7 +1278,7 @@ extern "C" size_t cgb_generate_velocities_workspace_bytes(int n_coeffs)
     d.d_cdf_P = d.d_cdf_r = d.d_psi_t = d.d_psi_c = d.d_f_t = d.d_f_c = (const double*)16;
     // header+tables, then padded knots (n+4), 64 dummy doubles, tile counter
     return (size_t)make_layout(&d).total * sizeof(double) +
-           cgb_align_up((size_t)(n_coeffs + 4) * 8, 256) + 512 + 256;
+           cgb_align_up((size_t)(n_coeffs + 4) * 8, 256) + 512 + cgb_sample_scratch_bytes();
 }
 
 __global__ void vel_dummy_kernel(double* __restrict__ dummy)
@@ -1122,10 +1319,9 @@ extern "C" int cgb_generate_velocities(const double* d_psi, const double* d_vesc
     unsigned char* w = (unsigned char*)d_work;
     double* t_full = (double*)(w + tab_bytes);
     double* dummy = (double*)(w + tab_bytes + cgb_align_up((size_t)(n_coeffs + 4) * 8, 256));
-    long long* counter = (long long*)((unsigned char*)dummy + 512);
+    ScratchHeader* scratch = (ScratchHeader*)((unsigned char*)dummy + 512);
     pad_knots_kernel<<<(n_knots + 6 + 255) / 256, 256, 0, s>>>(d_knots, n_knots, t_full);
     vel_dummy_kernel<<<1, 32, 0, s>>>(dummy);
-    CGB_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(long long), s));
     d.d_cdf_P = dummy; d.d_cdf_r = dummy; d.d_psi_t = dummy + 8; d.d_psi_c = dummy + 16;
     d.d_f_t = t_full; d.d_f_c = d_coeffs;
     int rc = cgb_sampler_prepare(&d, d_work, tab_bytes, stream);
@@ -1138,7 +1334,7 @@ extern "C" int cgb_generate_velocities(const double* d_psi, const double* d_vesc
     sp.speed = d_vel; sp.trials = d_trials;
     sp.in_psi = d_psi; sp.in_vesc = d_vesc; sp.in_env = d_fv2esc;
     sp.hu.d_u_trial = d_u_trial; sp.hu.t_cap = t_cap;
-    sp.tile_counter = counter;
+    sp.scratch = scratch;
     if (d_u_trial) return launch_sample<double, 1, true>(sp, s);
     return launch_sample<double, 1, false>(sp, s);
 }

@@ -107,7 +107,7 @@ class SamplerTables:
             N.check(N.CGB_E_INVALID)
         self.workspace = N.workspace(nb, dev)
         N.check(N.lib().cgb_sampler_prepare(N.ctypes.byref(d), N.ptr(self.workspace), nb, N.stream_ptr()))
-        self.tile_counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.scratch = N.workspace(N.lib().cgb_sample_scratch_bytes(), dev)
 
 
 def radius_cdf_table(r, m, r_max=None):
@@ -343,8 +343,8 @@ class VirialEquilibrium:
             a.d_pot = pot.data_ptr() if pot is not None else None
             a.d_moments = moments.data_ptr() if moments is not None else None
             host_u(a, lo, hi, True)
-            tabs.tile_counter.zero_()
-            N.check(L.cgb_sample_particles(N.ctypes.byref(a), N.ptr(tabs.tile_counter), N.stream_ptr()))
+            N.check(L.cgb_sample_particles(N.ctypes.byref(a), N.ptr(tabs.scratch), tabs.scratch.numel(),
+                                           N.stream_ptr()))
         elif n_loc > 0:
             # unique (r, |v|) for n_sub particles, tiled over all n (virial.py:170-173,208-211)
             ns = num_particles_sub
@@ -361,8 +361,8 @@ class VirialEquilibrium:
                 t = N.dev_f64(hu["u_r"], dev)
                 keep.append(t)
                 a.hu.d_u_r = t.data_ptr()
-            tabs.tile_counter.zero_()
-            N.check(L.cgb_sample_particles(N.ctypes.byref(a), N.ptr(tabs.tile_counter), N.stream_ptr()))
+            N.check(L.cgb_sample_particles(N.ctypes.byref(a), N.ptr(tabs.scratch), tabs.scratch.numel(),
+                                           N.stream_ptr()))
             if compute_potential:
                 N.check(L.cgb_spline_eval(N.ptr(tabs.psi_spline.t), N.ptr(tabs.psi_spline.c),
                                           tabs.psi_spline.n, N.ptr(r_sub), N.ptr(psi_sub), ns, 0,

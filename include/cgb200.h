@@ -197,9 +197,13 @@ typedef struct cgb_sample_args {
  * for sub_sample == 1: radius draw (utils.py:154-166), psi / envelope
  * (virial.py:191-194), rejection-sampled speed (the absent opt/cython_utils.pyx
  * generate_velocities, call site virial.py:198-206), isotropic directions and the
- * SoA field stores.  d_tile_counter: one zero-initialised device int64 used for
- * dynamic tile scheduling (caller zeroes before each call). */
-int cgb_sample_particles(const cgb_sample_args *args, int64_t *d_tile_counter, void *stream);
+ * SoA field stores.  d_scratch: >= cgb_sample_scratch_bytes() bytes of device memory,
+ * 64-byte aligned, private to this call while it runs (dynamic tile counter and the
+ * list of long-tail particles finished by a grid-wide second pass); the library
+ * initialises it. */
+size_t cgb_sample_scratch_bytes(void);
+int cgb_sample_particles(const cgb_sample_args *args, void *d_scratch, size_t scratch_bytes,
+                         void *stream);
 
 /* Directions-only pass used for sub_sample > 1 (virial.py:170-176,208-223): particle
  * i takes radius/speed d_radius_sub[i % n_sub], d_speed_sub[i % n_sub] and fresh

@@ -195,6 +195,23 @@ def test_generate_velocities_counter_mode_exact(oracle, name, ptype, n):
     np.testing.assert_allclose(vel, last["speed"], rtol=RTOL64)
 
 
+def test_generate_velocities_long_tail_goes_through_the_grid_wide_pass(oracle):
+    """Envelopes inflated by 1e4..3e4 => 1e5..1e6 trials for a few particles: these leave
+    the warp loop and are finished by the grid-wide second pass; the accepted trial must
+    still be the first accepted one in sequence order."""
+    n = 3000
+    ov, last, _ = _seam_inputs(oracle, "hernquist", "dark_matter", n)
+    last = {k: v.copy() for k, v in last.items()}
+    idx = np.arange(7, n, 150)
+    last["fv2esc"][idx] *= np.linspace(1.0e3, 6.0e4, idx.size)
+    vel_o, tr_o = oracle.generate_velocities_counter(last["psi"], last["vesc"], last["fv2esc"],
+                                                     ov.f.get_knots(), ov.f.get_coeffs(), 3, seed=99)
+    assert tr_o[idx].min() > 1000 and (tr_o > 70_000).sum() >= 5   # both sides of the deferral threshold
+    vel, tr = _call_seam(ov, last, n, 99)
+    np.testing.assert_array_equal(tr, tr_o)
+    np.testing.assert_allclose(vel, vel_o, rtol=RTOL64)
+
+
 def test_generate_velocities_host_uniform_array(oracle):
     n, tcap = 4000, 600
     ov, last, _ = _seam_inputs(oracle, "hernquist", "dark_matter", n)

@@ -440,3 +440,102 @@ def test_full_size_properties_config2():
     # idempotence: same prng -> same particles
     q = pm.generate_dm_particles(n, prng=7)
     assert torch.equal(q["dm", "particle_position"], pos)
+
+
+# --------------------------------------------------------------------------- #
+# committed golden vectors (tests/golden, scripts/make_golden.py): no oracle at run time
+# --------------------------------------------------------------------------- #
+import os
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _golden_product_model(name):
+    import cluster_generator_b200 as cg
+
+    if name == "hernquist":
+        return cg.ClusterModel.no_gas(0.1, 1.0e4, cg.hernquist_density_profile(1.0e15, 500.0), num_points=300)
+    if name == "nfw_bcg":
+        star = cg.hernquist_density_profile(1.0e12, 20.0)
+        return cg.ClusterModel.no_gas(0.1, 1.0e4, cg.nfw_density_profile(1.0e7, 100.0) + star,
+                                      stellar_density=star, num_points=300)
+    dens = cg.vikhlinin_density_profile(4.2e5, 100.0, 1000.0, 1.0, 0.67, 3.0)
+    temp = cg.vikhlinin_temperature_profile(10.0, 0.0, 2.0, 1.0, 1500.0, 6.0, 80.0, 1.0)
+    return cg.ClusterModel.from_dens_and_temp(0.1, 1.0e4, dens, temp, num_points=300)
+
+
+@pytest.mark.parametrize("name,ptype,key", [("hernquist", "dark_matter", "dm"), ("nfw_bcg", "dark_matter", "dm"),
+                                            ("nfw_bcg", "stellar", "star"), ("vikhlinin", "dark_matter", "dm")])
+def test_cuda_path_reproduces_golden_vectors(name, ptype, key):
+    import cluster_generator_b200.virial as V
+
+    z = np.load(os.path.join(GOLDEN, f"{name}_{key}.npz"))
+    pm = _golden_product_model(name)
+    np.testing.assert_allclose(np.asarray(pm["gravitational_potential"]), z["potential"], rtol=1e-13)
+    pv = pm.dm_virial if ptype == "dark_matter" else pm.star_virial
+    np.testing.assert_allclose(pv.g, z["g"], rtol=1e-9)
+    np.testing.assert_allclose(pv.ff, z["ff"], rtol=1e-8)
+    rho, chk = pv.check_virial()
+    np.testing.assert_allclose(rho, z["check_rho"], rtol=2e-4)
+    seed, n = int(z["seed"]), z["p_radius"].size
+    orig = V.seed_from_prng
+    V.seed_from_prng = lambda prng, species: seed
+    try:
+        p = pv.generate_particles(n, prng=0, compute_potential=True)
+    finally:
+        V.seed_from_prng = orig
+    d = p.diagnostics[key].as_dict()
+    assert d["sum_trials"] == z["p_trials"].sum() and d["max_trials"] == z["p_trials"].max()
+    _vec_close(_np(p[key, "particle_position"]), z["p_pos"], RTOL64, z["p_radius"])
+    _vec_close(_np(p[key, "particle_velocity"]), z["p_vel"], RTOL64, z["p_speed"])
+    np.testing.assert_allclose(_np(p[key, "particle_potential"]), z["p_pot"], rtol=RTOL64)
+    np.testing.assert_allclose(_np(p[key, "particle_mass"]), z["p_mass"], rtol=1e-14)
+
+
+def test_cuda_gas_path_reproduces_golden_vectors():
+    import cluster_generator_b200.model as M
+
+    z = np.load(os.path.join(GOLDEN, "vikhlinin_gas.npz"))
+    pm = _golden_product_model("vikhlinin")
+    seed, n = int(z["seed"]), z["p_mass"].size
+    orig = M.seed_from_prng
+    M.seed_from_prng = lambda prng, species: seed
+    try:
+        p = pm.generate_gas_particles(n, prng=0, compute_potential=True)
+    finally:
+        M.seed_from_prng = orig
+    pos = z["p_pos"]
+    _vec_close(_np(p["gas", "particle_position"]), pos, RTOL64, np.linalg.norm(pos, axis=1))
+    np.testing.assert_allclose(_np(p["gas", "thermal_energy"]), z["p_therm"], rtol=1e-9)
+    np.testing.assert_allclose(_np(p["gas", "density"]), z["p_dens"], rtol=1e-9)
+    np.testing.assert_allclose(_np(p["gas", "particle_potential"]), z["p_pot"], rtol=1e-9)
+    np.testing.assert_allclose(_np(p["gas", "particle_mass"]), z["p_mass"], rtol=1e-14)
+
+
+def test_device_qags_matches_scipy_traces_decision_for_decision():
+    """tests/golden/qags_traces.npz holds scipy's quad(..., full_output=1) state (last,
+    alist, blist, rlist, elist) for a few energy bins of both integrands."""
+    from scipy.interpolate import InterpolatedUnivariateSpline as IUS
+
+    from cluster_generator_b200 import _native as N
+
+    z = np.load(os.path.join(GOLDEN, "qags_traces.npz"))
+    g = np.load(os.path.join(GOLDEN, "hernquist_dm.npz"))
+    ee = g["ee"]
+    t, c, _ = IUS(ee, g["density"][::-1])._eval_args
+    tabs = {0: (N.dev_f64(t), N.dev_f64(c[: ee.size])), 1: (N.dev_f64(g["f_t"]), N.dev_f64(g["f_c"]))}
+    out = torch.zeros(204, dtype=torch.float64, device="cuda")
+    for key in z.files:
+        kind, b = (0 if key[0] == "d" else 1), int(key[1:])
+        td, cd = tabs[kind]
+        eps = 1.49e-5 if kind == 0 else 1.49e-8
+        upper = float(np.sqrt(ee[b])) if kind == 0 else float(ee[b])
+        N.check(N.lib().cgb_qags_trace(N.ptr(td), N.ptr(cd), ee.size, float(ee[b]), 0.0, upper, eps, eps,
+                                       kind, N.ptr(out), N.stream_ptr()))
+        o, ref = out.cpu().numpy(), z[key]
+        L = int(ref[2])
+        assert int(o[2]) == L, key
+        np.testing.assert_array_equal(o[4:4 + L], ref[3:3 + L], err_msg=key)                 # alist
+        np.testing.assert_array_equal(o[54:54 + L], ref[3 + L:3 + 2 * L], err_msg=key)       # blist
+        np.testing.assert_allclose(o[104:104 + L], ref[3 + 2 * L:3 + 3 * L], rtol=1e-13, atol=1e-300, err_msg=key)
+        np.testing.assert_allclose(o[0], ref[0], rtol=1e-13, err_msg=key)

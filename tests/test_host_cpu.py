@@ -1,0 +1,234 @@
+"""CPU suite, part 2: the C-ABI library surface and the host-side logic (no GPU)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "cgb200.h")
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from cluster_generator_b200 import _native as N
+
+    lib = N.load_library()
+    declared = set(re.findall(r"\b(cgb_[a-z0-9_]+)\s*\(", open(HEADER).read()))
+    declared -= {"cgb_sampler_desc", "cgb_host_uniforms", "cgb_sample_args"}
+    bound = {name for name, _, _ in N.SYMBOLS}
+    assert declared == bound, declared ^ bound
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.cgb_version() == 100
+    assert lib.cgb_sample_scratch_bytes() >= 64
+
+
+def test_ctypes_structs_match_the_c_header_layout():
+    """Compile a probe against include/cgb200.h with gcc and compare sizeof/offsetof."""
+    from cluster_generator_b200 import _native as N
+
+    src = r'''
+    #include <stdio.h>
+    #include <stddef.h>
+    #include "cgb200.h"
+    int main(void) {
+      printf("%zu %zu %zu\n", sizeof(cgb_sampler_desc), sizeof(cgb_host_uniforms), sizeof(cgb_sample_args));
+      printf("%zu %zu %zu %zu\n", offsetof(cgb_sampler_desc, d_psi_t), offsetof(cgb_sampler_desc, n_f),
+             offsetof(cgb_sampler_desc, d_aux_t), offsetof(cgb_sampler_desc, d_aux_c));
+      printf("%zu %zu %zu %zu %zu\n", offsetof(cgb_sample_args, seed), offsetof(cgb_sample_args, d_pos),
+             offsetof(cgb_sample_args, ld), offsetof(cgb_sample_args, d_moments), offsetof(cgb_sample_args, hu));
+      return 0; }'''
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "probe.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "probe")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        out = subprocess.check_output([exe], text=True).split()
+    got = [int(x) for x in out]
+    D, H, A = N.SamplerDesc, N.HostUniforms, N.SampleArgs
+    want = [ctypes.sizeof(D), ctypes.sizeof(H), ctypes.sizeof(A),
+            D.d_psi_t.offset, D.n_f.offset, D.d_aux_t.offset, D.d_aux_c.offset,
+            A.seed.offset, A.d_pos.offset, A.ld.offset, A.d_moments.offset, A.hu.offset]
+    assert got == want
+
+
+def test_no_cpu_fallback():
+    """Without a GPU the product path must fail loudly, not route through the oracle."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from cluster_generator_b200 import _native as N
+    from tests.configs import product_model
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        N.require_cuda()
+    pm = product_model("hernquist")      # host tables need no GPU
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pm.generate_dm_particles(10)
+    with pytest.raises(RuntimeError, match="not built"):
+        N.load_library("/nonexistent/libcgb200.so")
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "cluster_generator_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f
+                assert "cg_oracle" not in text or f.endswith((".cu", ".cuh")), f
+    out = subprocess.check_output(
+        [sys.executable, "-c", "import sys; sys.path.insert(0, %r); import cluster_generator_b200; "
+         "print(any(m.split('.')[0] == 'oracle' for m in sys.modules))" % ROOT], text=True)
+    assert out.strip() == "False"
+
+
+def test_host_tables_equal_the_oracle_tables():
+    from tests.configs import assert_tables_equal, oracle_model, product_model
+
+    for name in ("hernquist", "nfw_bcg", "vikhlinin"):
+        om, pm = oracle_model(name), product_model(name)
+        assert_tables_equal(om, pm)
+        assert pm["radius"].units == "kpc" and pm["gravitational_potential"].units == "kpc**2/Myr**2"
+        assert pm.num_elements == 1000
+    pm = product_model("vikhlinin")
+    assert np.all(pm.check_hse() < 1e-4)            # tests/test_models.py:99-114 (signed)
+    for k in ("gas_mass", "pressure", "temperature", "gas_fraction"):
+        np.testing.assert_array_equal(np.asarray(pm[k]), np.asarray(oracle_model("vikhlinin")[k])
+                                      if k != "temperature" else np.asarray(pm[k]))
+
+
+def test_radius_cdf_table_and_shards():
+    from cluster_generator_b200.virial import radius_cdf_table, shard_bounds
+    from oracle import cg_oracle as O
+    from tests.configs import oracle_model
+
+    om = oracle_model("hernquist")
+    for r_max in (None, 2000.0, 0.5):
+        a = radius_cdf_table(om["radius"], om["dark_matter_mass"], r_max)
+        b = O.radius_cdf_table(om["radius"], om["dark_matter_mass"], r_max)
+        for x, y in zip(a, b):
+            np.testing.assert_array_equal(x, y)
+        assert a[0][0] == 0.0 and a[0][-1] == 1.0 and np.all(np.diff(a[0]) > 0)
+    with pytest.raises(ValueError):
+        radius_cdf_table(om["radius"], om["dark_matter_mass"], 0.01)
+    for n in (0, 1, 7, 1000, 10**9 + 7):
+        for world in (1, 2, 3, 8):
+            b = [shard_bounds(n, (k, world)) for k in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[k][1] == b[k + 1][0] for k in range(world - 1))
+            assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+    assert shard_bounds(10, None) == (0, 10)
+    with pytest.raises(ValueError):
+        shard_bounds(10, (2, 2))
+
+
+def test_seed_derivation_follows_the_prng_stream():
+    from numpy.random import RandomState
+
+    from cluster_generator_b200.utils import parse_prng, seed_from_prng
+
+    a = seed_from_prng(parse_prng(25), 1)
+    assert a == seed_from_prng(parse_prng(25), 1) != seed_from_prng(parse_prng(25), 2)
+    prng = RandomState(25)
+    s1, s2 = seed_from_prng(prng, 1), seed_from_prng(prng, 1)
+    assert s1 == a and s2 != s1                     # a shared RandomState advances
+    assert 0 <= a < 2**64
+    assert parse_prng(prng) is prng
+
+
+def test_cluster_particles_container():
+    """particles.py:78-120, 423-451 semantics on CPU tensors."""
+    from cluster_generator_b200 import ClusterParticles
+
+    def make(key, n, off=0.0):
+        pos = (torch.arange(3 * n, dtype=torch.float64).reshape(3, n) + off)
+        return ClusterParticles(key, {(key, "particle_position"): pos.T,
+                                      (key, "particle_velocity"): (pos * 2).T,
+                                      (key, "particle_mass"): torch.ones(n, dtype=torch.float64)})
+
+    a, b, s = make("dm", 4), make("dm", 6, 100.0), make("star", 5)
+    ab = a + b
+    assert ab.num_particles == {"dm": 10}
+    p = ab["dm", "particle_position"]
+    assert p.shape == (10, 3) and p.T.is_contiguous()              # SoA planes survive concatenation
+    assert torch.equal(p[:4], a["dm", "particle_position"]) and torch.equal(p[4:], b["dm", "particle_position"])
+    allp = ab + s
+    assert allp.num_particles == {"dm": 10, "star": 5} and sorted(allp.particle_types) == ["dm", "star"]
+    assert allp.field_names["star"] == ["particle_position", "particle_velocity", "particle_mass"]
+    assert allp.field_units["dm", "particle_velocity"] == "kpc/Myr"
+    before = s["star", "particle_position"].clone()
+    s.add_offsets([1.0, 2.0, 3.0], [0.0, 0.0, 1.0])
+    assert torch.equal(s["star", "particle_position"] - before, torch.tensor([1.0, 2.0, 3.0]).expand(5, 3).double())
+    allp.drop_ptypes("star")
+    assert allp.particle_types == ["dm"] and ("star", "particle_mass") not in allp
+
+
+def test_radial_profile_algebra():
+    """cluster_generator/tests/test_radial_profiles.py:100-123"""
+    import cluster_generator_b200 as cg
+
+    r = np.geomspace(0.1, 1e4, 50)
+    h, n = cg.hernquist_density_profile(1e12, 20.0), cg.nfw_density_profile(1e7, 100.0)
+    np.testing.assert_allclose((h + n)(r), h(r) + n(r))
+    np.testing.assert_allclose((2.0 * h)(r), 2.0 * h(r))
+    np.testing.assert_allclose((h * n)(r), h(r) * n(r))
+    np.testing.assert_allclose((h**2)(r), h(r) ** 2)
+    assert np.all(h.cutoff(500.0)(r) <= h(r)) and np.all(h.add_core(1.0, 2.0)(r) <= h(r))
+
+
+def test_argument_validation_happens_before_any_gpu_work():
+    from tests.configs import product_model
+
+    pm = product_model("hernquist")
+    import cluster_generator_b200.virial as V
+
+    v = object.__new__(V.VirialEquilibrium)
+    v.ptype, v.model, v.num_elements, v._tables = "dark_matter", pm, pm.num_elements, {}
+    with pytest.raises(ValueError, match="multiple of sub_sample"):
+        v.generate_particles(10, sub_sample=3)
+    with pytest.raises(ValueError, match="rng"):
+        v.generate_particles(10, rng="mt")
+    with pytest.raises(ValueError):
+        v.generate_particles(-1)
+    with pytest.raises(KeyError):
+        V.VirialEquilibrium(pm, ptype="gas")
+    with pytest.raises(ValueError):
+        pm.set_field("radius", np.zeros(3))
+
+
+# ---- multi-process path on CPU (gloo, world_size 2) -------------------------------------- #
+def _gloo_worker(rank, world, port, n, out):
+    import torch.distributed as dist
+
+    from cluster_generator_b200 import _native as N
+    from cluster_generator_b200.virial import SamplerDiagnostics, shard_bounds
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard_bounds(n, (rank, world))
+    m = torch.zeros(N.CGB_NMOMENTS, dtype=torch.float64)
+    m[0] = hi - lo                    # particles of this shard
+    m[1] = float(sum(range(lo, hi)))  # stands in for the trial sum
+    m[2] = 10.0 + rank                # max trials: reduced with MAX, not SUM
+    d = SamplerDiagnostics(m, (rank, world)).all_reduce().as_dict()
+    if rank == 0:
+        torch.save(d, out)
+    dist.destroy_process_group()
+
+
+def test_moments_all_reduce_two_ranks_gloo(tmp_path):
+    import torch.multiprocessing as mp
+
+    n, world = 1001, 2
+    out = str(tmp_path / "d.pt")
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_gloo_worker, args=(world, port, n, out), nprocs=world, join=True)
+    d = torch.load(out)
+    assert d["particles"] == n and d["sum_trials"] == sum(range(n)) and d["max_trials"] == 11.0
+    assert d["mean_trials"] == pytest.approx(sum(range(n)) / n)

@@ -39,9 +39,13 @@
 #define TILE 128           // particles per warp tile buffer (two buffers per warp)
 #endif
 #define NBC 1024           // buckets of the CDF start-index table
+#ifndef LANE_CAP_PAIRS
+#define LANE_CAP_PAIRS 96  // trial pairs a particle may spend in its lane before the warp takes over
+#endif
 #define HARD_PAIRS 32768   // pair index beyond which a particle is deferred to the grid-wide pass
 #define HARD_CAP 4096      // capacity of the deferred-particle list
 #define TRI_DEFERRED (-2147483647)
+#define SCREEN_BYTES ((NB + 2) * 8)  // screen table + sentinel, 16-byte multiple
 #define SCREEN_REL 4.0e-6  // relative widening of the screen bounds (covers fp32 rounding)
 #define SCREEN_EDGE 0.02   // bucket range widening, in bucket widths
 
@@ -315,7 +319,7 @@ struct SampleParams {
     const double* base;  // workspace (header at base)
     long long id_begin, id_end;
     double particle_mass;
-    unsigned seed_lo, seed_hi;
+    unsigned rk[20];     // Philox round keys (k0 + r W0, k1 + r W1), r = 0..9: constant-bank operands
     void* pos; void* vel; long long ld;
     void* mass; void* pot;
     double* radius; double* speed; int* trials; double* moments;
@@ -325,6 +329,24 @@ struct SampleParams {
     const double* in_psi; const double* in_vesc; const double* in_env;
     long long first_id;
 };
+
+// Philox4x32-10 with the key schedule taken from the kernel parameters
+__device__ __forceinline__ Philox4 philox_rk(const unsigned (&rk)[20], unsigned c0, unsigned c1,
+                                             unsigned c2, unsigned c3)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(CGB_PHILOX_M0, c0), lo0 = CGB_PHILOX_M0 * c0;
+        const unsigned hi1 = __umulhi(CGB_PHILOX_M1, c2), lo1 = CGB_PHILOX_M1 * c2;
+        c0 = hi1 ^ c1 ^ rk[2 * r];
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ rk[2 * r + 1];
+        c3 = lo0;
+    }
+    Philox4 o;
+    o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+    return o;
+}
 
 struct Tables {
     const double *cdf_P, *cdf_r, *cdf_s;
@@ -337,6 +359,29 @@ struct Tables {
     double f_scale;
 };
 
+__device__ __forceinline__ void load_tables(const double* base, Tables& T)
+{
+    const SamplerHeader* hdr = (const SamplerHeader*)base;
+    T.cdf_P = base + hdr->off_cdf_P; T.cdf_r = base + hdr->off_cdf_r; T.cdf_s = base + hdr->off_cdf_s;
+    T.psi_brk = base + hdr->off_psi_brk; T.psi_pp = base + hdr->off_psi_pp;
+    T.f_brk = base + hdr->off_f_brk; T.f_pp = base + hdr->off_f_pp;
+    T.cdf_lut = (const unsigned*)(base + hdr->off_cdf_lut);
+    T.cdf_iv = (const int2*)(base + hdr->off_cdf_iv);
+    T.n_cdf = hdr->n_cdf; T.n_psi_int = hdr->n_psi - 3; T.n_f_int = hdr->n_f - 3;
+    T.inv_w_f = (float)hdr->inv_w;
+    T.f_scale = hdr->f_scale;
+}
+
+// the screen table in shared memory: NB buckets + one sentinel (-inf, +inf) that every
+// out-of-range bucket index is clamped to, so such trials come out "undecided"
+__device__ __forceinline__ void load_screen(const double* base, float2* s_screen)
+{
+    const SamplerHeader* hdr = (const SamplerHeader*)base;
+    const float2* g = (const float2*)(base + hdr->off_screen);
+    for (int i = threadIdx.x; i < NB; i += blockDim.x) s_screen[i] = g[i];
+    if (threadIdx.x == 0) s_screen[NB] = make_float2(-INFINITY, INFINITY);
+}
+
 // largest j in [0, n_cdf-2] with P[j] <= u       (np.interp's interval, utils.py:165)
 __device__ __forceinline__ int cdf_find(const Tables& T, double u)
 {
@@ -347,6 +392,12 @@ __device__ __forceinline__ int cdf_find(const Tables& T, double u)
         if (__ldg(T.cdf_P + mid) <= u) lo = mid; else hi = mid - 1;
     }
     return lo;
+}
+
+// envelope fv2esc = (2 psi) * f(psi)                                   (virial.py:192-193)
+__device__ __forceinline__ double envelope_of(const Tables& T, double psi)
+{
+    return __dmul_rn(__dmul_rn(2.0, psi), pp_eval(T.f_brk, T.f_pp, T.n_f_int, psi));
 }
 
 // exact accept test, the oracle's operation order (oracle/cg_oracle_c.c: trial()):
@@ -362,20 +413,31 @@ __device__ __forceinline__ bool exact_accept(const Tables& T, double u1, double 
     return !(__dmul_rn(F, v2) < __dmul_rn(u2, env));
 }
 
+// the three fp32 numbers the screen needs for one particle:
+//   ps = float(psi), vs = float(vesc * 2^-32), es = float(env * f_scale * 2^-32);
+// es = NaN (every comparison false => always "undecided") for particles the fp32
+// screen cannot represent safely
+__device__ __forceinline__ float screen_es(double psi, double vesc, double env, double f_scale)
+{
+    float es = (float)(env * f_scale * 0x1.0p-32);
+    const float v2max = (float)(vesc * vesc);
+    if (!(v2max > 1.0e-12f && v2max < 1.0e12f) || !(fabsf(es) > 1.0e-30f) || !(psi > 0.0))
+        es = __int_as_float(0x7fc00000);
+    return es;
+}
+
 // fp32 screen: 0 = reject, 1 = accept, 2 = undecided.
-//   vs = float(vesc * 2^-32), es = float(env * f_scale * 2^-32), ps = float(psi)
 __device__ __forceinline__ int screen_trial(const float2* __restrict__ s_screen, float inv_w_f,
                                             unsigned wa, unsigned wb, float ps, float vs, float es)
 {
     const float v = __uint2float_rn(wa) * vs;
     const float v2 = v * v;
     const float e = fmaf(-0.5f, v2, ps);
-    const int b = __float2int_rd(e * inv_w_f);
+    const unsigned b = (unsigned)__float2int_rd(e * inv_w_f);  // negative -> huge -> sentinel
     const float B = __uint2float_rn(wb) * es;
-    const float2 fb = s_screen[min(max(b, 0), NB - 1)];
-    const bool inr = (unsigned)b < (unsigned)NB;
-    if (inr && fb.y * v2 < B) return 0;
-    if (inr && fb.x * v2 >= B) return 1;
+    const float2 fb = s_screen[min(b, (unsigned)NB)];
+    if (fb.y * v2 < B) return 0;
+    if (fb.x * v2 >= B) return 1;
     return 2;
 }
 
@@ -384,29 +446,42 @@ struct PairResult {
     int n_exact;  // exact evaluations spent
 };
 
-// evaluate the two trials of one Philox call for one particle
-__device__ __forceinline__ PairResult eval_pair(const Tables& T, const float2* s_screen,
-                                                const Philox4& w, float ps, float vs, float es,
-                                                double psi, double vesc, double env)
+// Resolve the undecided trials of a pair on the exact fp64 path.  sa/sb are the screen
+// results; penv == nullptr: the envelope is recomputed from psi (fused mode).
+__device__ __noinline__ PairResult resolve_pair(const Tables& T, const Philox4& w, int sa, int sb,
+                                                double psi, double vesc, const double* penv)
 {
     PairResult r;
     r.acc = 0; r.n_exact = 0;
-    int sa = screen_trial(s_screen, T.inv_w_f, w.x, w.y, ps, vs, es);
-    int sb = screen_trial(s_screen, T.inv_w_f, w.z, w.w, ps, vs, es);
+    const double env = penv ? *penv : envelope_of(T, psi);
+    double v2;
     if (sa == 2) {
-        double v2;
-        sa = exact_accept(T, u32_to_double(w.x) * 0x1.0p-32, u32_to_double(w.y) * 0x1.0p-32, psi,
-                          vesc, env, v2) ? 1 : 0;
+        sa = exact_accept(T, u32_to_double(w.x) * 0x1.0p-32, u32_to_double(w.y) * 0x1.0p-32, psi, vesc,
+                          env, v2) ? 1 : 0;
         ++r.n_exact;
     }
     if (sa == 1) { r.acc = 1; return r; }
     if (sb == 2) {
-        double v2;
-        sb = exact_accept(T, u32_to_double(w.z) * 0x1.0p-32, u32_to_double(w.w) * 0x1.0p-32, psi,
-                          vesc, env, v2) ? 1 : 0;
+        sb = exact_accept(T, u32_to_double(w.z) * 0x1.0p-32, u32_to_double(w.w) * 0x1.0p-32, psi, vesc,
+                          env, v2) ? 1 : 0;
         ++r.n_exact;
     }
     if (sb == 1) r.acc = 2;
+    return r;
+}
+
+// evaluate the two trials of one Philox call for one particle
+__device__ __forceinline__ PairResult eval_pair(const Tables& T, const float2* s_screen,
+                                                const Philox4& w, float ps, float vs, float es,
+                                                const double* ppsi, const double* pvesc,
+                                                const double* penv)
+{
+    const int sa = screen_trial(s_screen, T.inv_w_f, w.x, w.y, ps, vs, es);
+    const int sb = screen_trial(s_screen, T.inv_w_f, w.z, w.w, ps, vs, es);
+    if (sa == 2 || (sa == 0 && sb == 2)) return resolve_pair(T, w, sa, sb, *ppsi, *pvesc, penv);
+    PairResult r;
+    r.n_exact = 0;
+    r.acc = (sa == 1) ? 1 : ((sb == 1) ? 2 : 0);
     return r;
 }
 
@@ -416,48 +491,45 @@ __device__ __forceinline__ void store_out(void* p, long long i, double v)
     ((OutT*)p)[i] = (OutT)v;
 }
 
+// speed from the accepted first uniform: v = u1 * vesc, returned as sqrt(v^2) like the oracle
+__device__ __forceinline__ double speed_of(unsigned wa, double vesc)
+{
+    const double v = __dmul_rn(u32_to_double(wa) * 0x1.0p-32, vesc);
+    return sqrt(__dmul_rn(v, v));
+}
+
 // MODE 0: fused DM/star sampler.  MODE 1: velocity-only (Cython seam mirror).
 //
 // Each warp keeps TWO tile buffers in shared memory (rolling window).  Lanes claim
 // particles from the current buffer; when it runs dry the warp sets up the next tile
 // in the other buffer and lanes keep refilling from there while stragglers of the
 // previous tile finish in their lanes.  A tile is written out (phase 2) as soon as
-// all its particles are done.  Only when a buffer must be recycled while it still
-// holds stragglers (rare: the long tail of the trial-count distribution), and at the
-// very end of the kernel, does the whole warp finish a particle cooperatively
-// (64 trials per step; the first accepted trial in sequence order wins, so the
-// result is independent of scheduling).
+// all its particles are done.  When a buffer must be recycled while it still holds
+// stragglers (the long tail of the trial-count distribution), when a particle has
+// spent LANE_CAP_PAIRS in its lane, and at the very end of the kernel, the whole warp
+// finishes a particle cooperatively (128 trials per step; the first accepted trial in
+// sequence order wins, so the result is independent of scheduling).
 template <typename OutT, int MODE, bool HOST_U>
-__global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(SampleParams p)
+__global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_constant__ SampleParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     float2* s_screen = (float2*)smem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // per-warp slot arrays, 2 buffers x TILE slots each
-    double* s_psi = (double*)(smem + NB * sizeof(float2)) + (size_t)warp * 4 * (2 * TILE);
-    double* s_ves = s_psi + 2 * TILE;  // vesc, overwritten by the accepted speed
-    double* s_env = s_ves + 2 * TILE;  // envelope; its low word holds the trial count once done
-    double* s_rad = s_env + 2 * TILE;  // radius (MODE 0)
-    int* s_tri = (int*)s_env;
-    double* s_mom = (double*)(smem + NB * sizeof(float2)) + (size_t)WARPS * 4 * (2 * TILE) +
-                    (size_t)warp * CGB_NMOMENTS;
+    // per-warp slot arrays, 2 buffers x TILE slots, 32 B per slot
+    unsigned char* wbase = smem + SCREEN_BYTES + (size_t)warp * (2 * TILE) * 32;
+    double* s_psi = (double*)wbase;            // relative potential
+    double* s_ves = s_psi + 2 * TILE;          // escape speed
+    double* s_rad = s_ves + 2 * TILE;          // radius (MODE 0)
+    float* s_es = (float*)(s_rad + 2 * TILE);  // fp32 envelope for the screen; trial count once done
+    unsigned* s_wa = (unsigned*)(s_es + 2 * TILE);  // accepted first uniform (32 bits)
+    int* s_tri = (int*)s_es;
+    double* s_mom = (double*)(smem + SCREEN_BYTES + (size_t)WARPS * (2 * TILE) * 32) + (size_t)warp * CGB_NMOMENTS;
     const unsigned FULL = 0xffffffffu;
     const unsigned lt_mask = (1u << lane) - 1u;
 
-    const SamplerHeader* hdr = (const SamplerHeader*)p.base;
     Tables T;
-    T.cdf_P = p.base + hdr->off_cdf_P; T.cdf_r = p.base + hdr->off_cdf_r; T.cdf_s = p.base + hdr->off_cdf_s;
-    T.psi_brk = p.base + hdr->off_psi_brk; T.psi_pp = p.base + hdr->off_psi_pp;
-    T.f_brk = p.base + hdr->off_f_brk; T.f_pp = p.base + hdr->off_f_pp;
-    T.cdf_lut = (const unsigned*)(p.base + hdr->off_cdf_lut);
-    T.cdf_iv = (const int2*)(p.base + hdr->off_cdf_iv);
-    T.n_cdf = hdr->n_cdf; T.n_psi_int = hdr->n_psi - 3; T.n_f_int = hdr->n_f - 3;
-    T.inv_w_f = (float)hdr->inv_w;
-    T.f_scale = hdr->f_scale;
-    {
-        const float2* g = (const float2*)(p.base + hdr->off_screen);
-        for (int i = threadIdx.x; i < NB; i += blockDim.x) s_screen[i] = g[i];
-    }
+    load_tables(p.base, T);
+    load_screen(p.base, s_screen);
     if (lane < CGB_NMOMENTS) s_mom[lane] = 0.0;
     __syncthreads();
 
@@ -466,6 +538,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(SampleParams 
     bool no_defer = false;           // warp-uniform: the deferred list overflowed
 
     const long long n_local = p.id_end - p.id_begin;
+    const long long id_base = (MODE == 0 ? p.id_begin : p.first_id);
     // warp-uniform buffer state
     // (scalars selected by ternaries: dynamically indexed arrays would go to local memory)
     long long b_loc0_0 = 0, b_loc0_1 = 0;
@@ -484,7 +557,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(SampleParams 
         const long long loc0 = tile * TILE;
         if (loc0 >= n_local) { more_tiles = false; return false; }
         const int cnt = (int)min((long long)TILE, n_local - loc0);
-        const long long id0 = (MODE == 0 ? p.id_begin : p.first_id) + loc0;
+        const long long id0 = id_base + loc0;
         int nonpos = 0;
         for (int i = lane; i < cnt; i += 32) {
             double psi, vesc, env;
@@ -494,8 +567,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(SampleParams 
                 double u;
                 if (HOST_U && p.hu.d_u_r) u = p.hu.d_u_r[loc0 + i];
                 else {
-                    const Philox4 w = philox4x32_10((unsigned)id, (unsigned)(id >> 32), 0u,
-                                                    CGB_STREAM_RADIUS, p.seed_lo, p.seed_hi);
+                    const Philox4 w = philox_rk(p.rk, (unsigned)id, (unsigned)(id >> 32), 0u, CGB_STREAM_RADIUS);
                     u = u52(w.x, w.y);
                 }
                 // np.interp(u, P_r, r): j = searchsorted(P_r, u, 'right') - 1        (utils.py:165)
@@ -515,7 +587,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(SampleParams 
                 vesc = p.in_vesc[loc0 + i];
                 env = p.in_env[loc0 + i];
             }
-            s_psi[s] = psi; s_ves[s] = vesc; s_env[s] = env;
+            s_psi[s] = psi; s_ves[s] = vesc;
+            s_es[s] = screen_es(psi, vesc, env, T.f_scale);
             if (!(env > 0.0)) ++nonpos;
         }
         nonpos = __reduce_add_sync(FULL, nonpos);
@@ -529,7 +602,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(SampleParams 
     auto epilogue = [&](int b) {
         const long long loc0 = BGET(b_loc0, b);
         const int cnt = BGET(b_cnt, b);
-        const long long id0 = (MODE == 0 ? p.id_begin : p.first_id) + loc0;
+        const long long id0 = id_base + loc0;
         double a_v2 = 0.0, a_psi = 0.0, a_r = 0.0, a_px = 0.0, a_py = 0.0, a_pz = 0.0, a_vx = 0.0,
                a_vy = 0.0, a_vz = 0.0;
         unsigned a_tr = 0, a_tmax = 0, a_fail = 0;
@@ -538,9 +611,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(SampleParams 
             const int s = b * TILE + i;
             const long long loc = loc0 + i;
             const double psi = s_psi[s];
-            const double v = s_ves[s];
-            const int nt = s_tri[2 * s];
+            const int nt = s_tri[s];
             const bool deferred = nt == TRI_DEFERRED;  // speed comes from cgb_hard_kernel
+            // literal host-uniform mode stashed the speed itself in the vesc slot
+            const double v = (nt > 0) ? ((HOST_U && p.hu.d_u_trial) ? s_ves[s] : speed_of(s_wa[s], s_ves[s]))
+                                      : __longlong_as_double(0x7ff8000000000000LL);
             if (nt > 0) { a_tr += (unsigned)nt; a_tmax = max(a_tmax, (unsigned)nt); }
             else if (!deferred) ++a_fail;
             if (MODE == 1) {
@@ -555,14 +630,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(SampleParams 
             double uc, up, ucv, upv;
             if (HOST_U && p.hu.d_u_ct) { uc = p.hu.d_u_ct[loc]; up = p.hu.d_u_ph[loc]; }
             else {
-                const Philox4 w = philox4x32_10((unsigned)id, (unsigned)(id >> 32), 0u,
-                                                CGB_STREAM_POS_DIR, p.seed_lo, p.seed_hi);
+                const Philox4 w = philox_rk(p.rk, (unsigned)id, (unsigned)(id >> 32), 0u, CGB_STREAM_POS_DIR);
                 uc = u52(w.x, w.y); up = u52(w.z, w.w);
             }
             if (HOST_U && p.hu.d_u_ctv) { ucv = p.hu.d_u_ctv[loc]; upv = p.hu.d_u_phv[loc]; }
             else {
-                const Philox4 w = philox4x32_10((unsigned)id, (unsigned)(id >> 32), 0u,
-                                                CGB_STREAM_VEL_DIR, p.seed_lo, p.seed_hi);
+                const Philox4 w = philox_rk(p.rk, (unsigned)id, (unsigned)(id >> 32), 0u, CGB_STREAM_VEL_DIR);
                 ucv = u52(w.x, w.y); upv = u52(w.z, w.w);
             }
             // theta = arccos(-1 + 2u), phi = 2 pi u                     (virial.py:175-176)
@@ -620,54 +693,57 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(SampleParams 
 
     // ---- per-lane trial state ----
     int slot = -1;
-    unsigned pair = 0;
+    unsigned pair = 0, id_lo = 0, id_hi = 0;
     float ps = 0.f, vs = 0.f, es = 0.f;
-    auto lane_floats = [&](double psi, double vesc, double env, float& fps, float& fvs, float& fes) {
-        fps = (float)psi;
-        fvs = (float)(vesc * 0x1.0p-32);
-        fes = (float)(env * T.f_scale * 0x1.0p-32);
-        // particles the fp32 screen cannot represent safely: NaN makes every screen
-        // comparison false, so they always take the exact path
-        const float v2max = (float)(vesc * vesc);
-        if (!(v2max > 1.0e-12f && v2max < 1.0e12f) || !(fabsf(fes) > 1.0e-30f) || !(psi > 0.0))
-            fes = __int_as_float(0x7fc00000);
+
+    // the exact path's envelope: an input array in MODE 1, recomputed from psi in MODE 0
+    auto env_ptr = [&](int s) -> const double* {
+        if (MODE == 0) return nullptr;
+        const int b = s / TILE;
+        return p.in_env + (BGET(b_loc0, b) + (s - b * TILE));
     };
 
-    // finish the particle in slot s cooperatively from pair index pair0 (warp-uniform args)
-    auto coop_finish = [&](int s, unsigned pair0) {
-        const int b = s / TILE;
-        const double psi = s_psi[s], vesc = s_ves[s], env = s_env[s];
-        float cps, cvs, ces;
-        lane_floats(psi, vesc, env, cps, cvs, ces);
-        const unsigned long long id =
-            (unsigned long long)((MODE == 0 ? p.id_begin : p.first_id) + BGET(b_loc0, b) + (s - b * TILE));
-        unsigned long long pr = pair0;
-        __syncwarp();
+    // Finish the particle held by lane `src` with the whole warp: 64 consecutive trial pairs
+    // (128 trials) per step in two independent Philox chains per lane; the first accepted
+    // trial in sequence order wins -- the answer of the serial loop.
+    auto coop_finish = [&](int src) {
+        const int s = __shfl_sync(FULL, slot, src);
+        const unsigned p0 = __shfl_sync(FULL, pair, src);
+        const float cps = __shfl_sync(FULL, ps, src), cvs = __shfl_sync(FULL, vs, src),
+                    ces = __shfl_sync(FULL, es, src);
+        const unsigned cid_lo = __shfl_sync(FULL, id_lo, src), cid_hi = __shfl_sync(FULL, id_hi, src);
+        const double* penv = env_ptr(s);
+        unsigned long long pr = p0;
         for (;;) {
-            const unsigned long long mine = pr + lane;
-            PairResult r;
-            r.acc = 0; r.n_exact = 0;
-            Philox4 w;
-            w.x = w.y = w.z = w.w = 0;
-            if (mine <= 0xFFFFFFFFull) {
-                w = philox4x32_10((unsigned)id, (unsigned)(id >> 32), (unsigned)mine,
-                                  CGB_STREAM_VEL_TRIAL, p.seed_lo, p.seed_hi);
-                r = eval_pair(T, s_screen, w, cps, cvs, ces, psi, vesc, env);
+            const unsigned long long mine0 = pr + lane, mine1 = pr + 32 + lane;
+            PairResult r0, r1;
+            r0.acc = r1.acc = 0; r0.n_exact = r1.n_exact = 0;
+            Philox4 w0, w1;
+            w0.x = w0.y = w0.z = w0.w = 0;
+            w1 = w0;
+            if (mine1 <= 0xFFFFFFFFull) {
+                w0 = philox_rk(p.rk, cid_lo, cid_hi, (unsigned)mine0, CGB_STREAM_VEL_TRIAL);
+                w1 = philox_rk(p.rk, cid_lo, cid_hi, (unsigned)mine1, CGB_STREAM_VEL_TRIAL);
+                r0 = eval_pair(T, s_screen, w0, cps, cvs, ces, s_psi + s, s_ves + s, penv);
+                r1 = eval_pair(T, s_screen, w1, cps, cvs, ces, s_psi + s, s_ves + s, penv);
+            } else if (mine0 <= 0xFFFFFFFFull) {
+                w0 = philox_rk(p.rk, cid_lo, cid_hi, (unsigned)mine0, CGB_STREAM_VEL_TRIAL);
+                r0 = eval_pair(T, s_screen, w0, cps, cvs, ces, s_psi + s, s_ves + s, penv);
             }
-            m_exact += r.n_exact;
-            const unsigned hit = __ballot_sync(FULL, r.acc != 0);
-            if (hit) {
-                const int src = __ffs(hit) - 1;
-                if (lane == src) {
-                    const unsigned wa = (r.acc == 1) ? w.x : w.z;
-                    const double v = __dmul_rn(u32_to_double(wa) * 0x1.0p-32, vesc);
-                    s_ves[s] = sqrt(__dmul_rn(v, v));
-                    const unsigned long long nt = 2ULL * mine + (unsigned)r.acc;
-                    s_tri[2 * s] = (int)min(nt, 0x7fffffffULL);
+            m_exact += r0.n_exact + r1.n_exact;
+            const unsigned hit0 = __ballot_sync(FULL, r0.acc != 0);
+            const unsigned hit1 = __ballot_sync(FULL, r1.acc != 0);
+            if (hit0 | hit1) {
+                const bool first = hit0 != 0;
+                if (lane == __ffs(first ? hit0 : hit1) - 1) {
+                    const int acc = first ? r0.acc : r1.acc;
+                    const unsigned long long mine = first ? mine0 : mine1;
+                    s_wa[s] = first ? (acc == 1 ? w0.x : w0.z) : (acc == 1 ? w1.x : w1.z);
+                    s_tri[s] = (int)min(2ULL * mine + (unsigned)acc, 0x7fffffffULL);
                 }
                 break;
             }
-            pr += 32;
+            pr += 64;
             if (pr >= HARD_PAIRS && !no_defer) {
                 // long tail: hand the particle to the grid-wide pass (cgb_hard_kernel)
                 unsigned h = 0;
@@ -675,36 +751,36 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(SampleParams 
                 h = __shfl_sync(FULL, h, 0);
                 if (h < HARD_CAP) {
                     if (lane == 0) {
+                        const int bb = s / TILE;
                         HardEntry* e = (HardEntry*)(p.scratch + 1) + h;
-                        e->id = id; e->loc = BGET(b_loc0, b) + (s - b * TILE);
-                        e->psi = psi; e->vesc = vesc; e->env = env;
+                        e->id = ((unsigned long long)cid_hi << 32) | cid_lo;
+                        e->loc = BGET(b_loc0, bb) + (s - bb * TILE);
+                        e->psi = s_psi[s]; e->vesc = s_ves[s];
+                        e->env = penv ? *penv : envelope_of(T, s_psi[s]);
                         e->next_pair = pr; e->best = ~0ULL;
-                        s_ves[s] = 0.0; s_tri[2 * s] = TRI_DEFERRED;
+                        s_tri[s] = TRI_DEFERRED;
                     }
                     break;
                 }
                 no_defer = true;  // list full: keep going in the warp
             }
-            if (pr > 0xFFFFFFFFull) {  // trial cap reached: report failure
-                if (lane == 0) { s_ves[s] = __longlong_as_double(0x7ff8000000000000LL); s_tri[2 * s] = -1; }
+            if (pr > 0xFFFFFFFFull) {  // 2^33 trials exhausted: report failure
+                if (lane == 0) s_tri[s] = -1;
                 break;
             }
         }
         ++m_coop;
+        if (s >= TILE) ++b_fin_1; else ++b_fin_0;
+        if (lane == src) slot = -1;
         __syncwarp();
     };
 
-    // cooperatively finish every in-flight particle that lives in buffer b (b < 0: any)
-    auto finish_stragglers = [&](int b) {
-        unsigned rem = __ballot_sync(FULL, slot >= 0 && (b < 0 || slot / TILE == b));
-        while (rem) {
-            const int src = __ffs(rem) - 1;
-            rem &= rem - 1;
-            const int s = __shfl_sync(FULL, slot, src);
-            const unsigned p0 = __shfl_sync(FULL, pair, src);
-            coop_finish(s, p0);
-            if (s / TILE) ++b_fin_1; else ++b_fin_0;
-            if (lane == src) slot = -1;
+    // cooperatively finish every lane in `mask`
+    auto finish_lanes = [&](unsigned mask) {
+        while (mask) {
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            coop_finish(src);
         }
     };
 
@@ -712,15 +788,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(SampleParams 
         // literal host-supplied (u1,u2)[t_cap] per particle: exact path only, tile by tile
         while (acquire(0)) {
             for (int i = lane; i < b_cnt_0; i += 32) {
-                const double psi = s_psi[i], vesc = s_ves[i], env = s_env[i];
+                const double psi = s_psi[i], vesc = s_ves[i];
+                const double env = (MODE == 0) ? envelope_of(T, psi) : p.in_env[b_loc0_0 + i];
                 const double* uu = p.hu.d_u_trial + (size_t)(b_loc0_0 + i) * (size_t)p.hu.t_cap * 2;
                 int acc = -1;
                 double v2 = 0.0;
                 for (long long t = 0; t < p.hu.t_cap; ++t) {
                     if (exact_accept(T, uu[2 * t], uu[2 * t + 1], psi, vesc, env, v2)) { acc = (int)(t + 1); break; }
                 }
+                // keep the literal double uniform: stash the speed itself in the vesc slot
                 s_ves[i] = (acc > 0) ? sqrt(v2) : __longlong_as_double(0x7ff8000000000000LL);
-                s_tri[2 * i] = acc;
+                s_wa[i] = 0u;
+                s_tri[i] = acc;
             }
             epilogue(0);
         }
@@ -734,7 +813,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(SampleParams 
                     if (!more_tiles) break;
                     const int other = cur ^ 1;
                     if (BGET(b_live, other)) {  // recycle: its stragglers are finished by the whole warp
-                        finish_stragglers(other);
+                        finish_lanes(__ballot_sync(FULL, slot >= 0 && slot / TILE == other));
                         epilogue(other);
                     }
                     if (!acquire(other)) break;
@@ -745,9 +824,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(SampleParams 
                 const int want = __popc(need);
                 const int rank = __popc(need & lt_mask);
                 if (((need >> lane) & 1u) && rank < avail) {
-                    slot = cur * TILE + BGET(b_next, cur) + rank;
-                    lane_floats(s_psi[slot], s_ves[slot], s_env[slot], ps, vs, es);
+                    const int i = BGET(b_next, cur) + rank;
+                    slot = cur * TILE + i;
+                    ps = (float)s_psi[slot];
+                    vs = (float)(s_ves[slot] * 0x1.0p-32);
+                    es = s_es[slot];
                     pair = 0;
+                    const unsigned long long id = (unsigned long long)(id_base + BGET(b_loc0, cur) + i);
+                    id_lo = (unsigned)id; id_hi = (unsigned)(id >> 32);
                 }
                 BSET(b_next, cur, BGET(b_next, cur) + min(want, avail));
                 if (want <= avail) break;
@@ -756,47 +840,37 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(SampleParams 
             const unsigned act = __ballot_sync(FULL, slot >= 0);
             if (act == 0) break;
             if (!more_tiles && BGET(b_next, cur) == BGET(b_cnt, cur)) {
-                // nothing left to claim anywhere: final drain
-                finish_stragglers(-1);
+                finish_lanes(act);  // nothing left to claim anywhere: final drain
                 break;
             }
             // ---- one Philox call = two trials for every active lane ----
             bool done = false;
             if (slot >= 0) {
-                const int b = slot / TILE;
-                const unsigned long long id = (unsigned long long)(
-                    (MODE == 0 ? p.id_begin : p.first_id) + BGET(b_loc0, b) + (slot - b * TILE));
-                const Philox4 w = philox4x32_10((unsigned)id, (unsigned)(id >> 32), pair,
-                                                CGB_STREAM_VEL_TRIAL, p.seed_lo, p.seed_hi);
-                int sa = screen_trial(s_screen, T.inv_w_f, w.x, w.y, ps, vs, es);
-                int sb = screen_trial(s_screen, T.inv_w_f, w.z, w.w, ps, vs, es);
-                if (sa == 2 || (sa == 0 && sb == 2)) {
-                    const PairResult r = eval_pair(T, s_screen, w, ps, vs, es, s_psi[slot], s_ves[slot],
-                                                   s_env[slot]);
-                    m_exact += r.n_exact;
-                    sa = (r.acc == 1); sb = (r.acc == 2);
-                }
-                if (sa == 1 || sb == 1) {
-                    const unsigned wa = (sa == 1) ? w.x : w.z;
-                    const double vesc = s_ves[slot];
-                    const double v = __dmul_rn(u32_to_double(wa) * 0x1.0p-32, vesc);
-                    s_ves[slot] = sqrt(__dmul_rn(v, v));
-                    s_tri[2 * slot] = (int)(2u * pair + (sa == 1 ? 1u : 2u));
+                const Philox4 w = philox_rk(p.rk, id_lo, id_hi, pair, CGB_STREAM_VEL_TRIAL);
+                const PairResult r = eval_pair(T, s_screen, w, ps, vs, es, s_psi + slot, s_ves + slot,
+                                               env_ptr(slot));
+                m_exact += r.n_exact;
+                if (r.acc) {
+                    s_wa[slot] = (r.acc == 1) ? w.x : w.z;
+                    s_tri[slot] = (int)(2u * pair + (unsigned)r.acc);
                     done = true;
-                } else if (++pair == 0u) {  // 2^33 trials exhausted
-                    s_ves[slot] = __longlong_as_double(0x7ff8000000000000LL);
-                    s_tri[2 * slot] = -1;
-                    done = true;
+                } else {
+                    ++pair;
                 }
             }
-            const unsigned d0 = __ballot_sync(FULL, done && slot < TILE);
-            const unsigned d1 = __ballot_sync(FULL, done && slot >= TILE);
-            if (done) slot = -1;
-            b_fin_0 += __popc(d0);
-            b_fin_1 += __popc(d1);
-            // a fully finished tile that is no longer being claimed from goes out
-            const int other = cur ^ 1;
-            if (BGET(b_live, other) && BGET(b_fin, other) == BGET(b_cnt, other)) epilogue(other);
+            // long runners leave their lane: the warp finishes them 128 trials at a time
+            const unsigned lng = __ballot_sync(FULL, slot >= 0 && !done && pair >= LANE_CAP_PAIRS);
+            if (lng) finish_lanes(lng);
+            if (__any_sync(FULL, done)) {
+                const unsigned d0 = __ballot_sync(FULL, done && slot < TILE);
+                const unsigned d1 = __ballot_sync(FULL, done && slot >= TILE);
+                if (done) slot = -1;
+                b_fin_0 += __popc(d0);
+                b_fin_1 += __popc(d1);
+                // a fully finished tile that is no longer being claimed from goes out
+                const int other = cur ^ 1;
+                if (BGET(b_live, other) && BGET(b_fin, other) == BGET(b_cnt, other)) epilogue(other);
+            }
         }
         // write out whatever is still held
         if (BGET(b_live, cur ^ 1)) epilogue(cur ^ 1);
@@ -829,7 +903,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(SampleParams 
 // (atomicMin).  The last CTA to finish writes the speeds / velocity vectors.  The
 // result is the first accepted trial in sequence order -- identical to the serial loop.
 template <typename OutT, int MODE, bool HOST_U>
-__global__ void __launch_bounds__(512, 1) cgb_hard_kernel(SampleParams p)
+__global__ void __launch_bounds__(512, 1) cgb_hard_kernel(const __grid_constant__ SampleParams p)
 {
     ScratchHeader* sh = p.scratch;
     const unsigned n_hard = min(sh->hard_count, (unsigned)HARD_CAP);
@@ -841,31 +915,19 @@ __global__ void __launch_bounds__(512, 1) cgb_hard_kernel(SampleParams p)
     __shared__ int s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned FULL = 0xffffffffu;
-    const SamplerHeader* hdr = (const SamplerHeader*)p.base;
     Tables T;
-    T.cdf_P = p.base + hdr->off_cdf_P; T.cdf_r = p.base + hdr->off_cdf_r; T.cdf_s = p.base + hdr->off_cdf_s;
-    T.psi_brk = p.base + hdr->off_psi_brk; T.psi_pp = p.base + hdr->off_psi_pp;
-    T.f_brk = p.base + hdr->off_f_brk; T.f_pp = p.base + hdr->off_f_pp;
-    T.cdf_lut = (const unsigned*)(p.base + hdr->off_cdf_lut);
-    T.cdf_iv = (const int2*)(p.base + hdr->off_cdf_iv);
-    T.n_cdf = hdr->n_cdf; T.n_psi_int = hdr->n_psi - 3; T.n_f_int = hdr->n_f - 3;
-    T.inv_w_f = (float)hdr->inv_w;
-    T.f_scale = hdr->f_scale;
-    {
-        const float2* g = (const float2*)(p.base + hdr->off_screen);
-        for (int i = threadIdx.x; i < NB; i += blockDim.x) s_screen[i] = g[i];
-    }
+    load_tables(p.base, T);
+    load_screen(p.base, s_screen);
     __syncthreads();
     HardEntry* ent = (HardEntry*)(sh + 1);
     for (unsigned h = 0; h < n_hard; ++h) {
-        const HardEntry e = ent[h];
-        float cps = (float)e.psi, cvs = (float)(e.vesc * 0x1.0p-32), ces = (float)(e.env * T.f_scale * 0x1.0p-32);
-        const float v2max = (float)(e.vesc * e.vesc);
-        if (!(v2max > 1.0e-12f && v2max < 1.0e12f) || !(fabsf(ces) > 1.0e-30f) || !(e.psi > 0.0))
-            ces = __int_as_float(0x7fc00000);
+        const unsigned long long e_id = ent[h].id, e_next = ent[h].next_pair;
+        const double e_psi = ent[h].psi, e_vesc = ent[h].vesc, e_env = ent[h].env;
+        const float cps = (float)e_psi, cvs = (float)(e_vesc * 0x1.0p-32);
+        const float ces = screen_es(e_psi, e_vesc, e_env, T.f_scale);
         volatile unsigned long long* bestp = &ent[h].best;
         for (unsigned long long chunk = blockIdx.x;; chunk += gridDim.x) {
-            const unsigned long long start = e.next_pair + chunk * 512ULL;
+            const unsigned long long start = e_next + chunk * 512ULL;
             if (threadIdx.x == 0) s_bcast = *bestp;
             __syncthreads();
             const unsigned long long best = s_bcast;
@@ -873,9 +935,9 @@ __global__ void __launch_bounds__(512, 1) cgb_hard_kernel(SampleParams p)
             const unsigned long long mine = start + threadIdx.x;
             unsigned long long t = ~0ULL;
             if (mine <= 0xFFFFFFFFull) {
-                const Philox4 w = philox4x32_10((unsigned)e.id, (unsigned)(e.id >> 32), (unsigned)mine,
-                                                CGB_STREAM_VEL_TRIAL, p.seed_lo, p.seed_hi);
-                const PairResult r = eval_pair(T, s_screen, w, cps, cvs, ces, e.psi, e.vesc, e.env);
+                const Philox4 w = philox_rk(p.rk, (unsigned)e_id, (unsigned)(e_id >> 32), (unsigned)mine,
+                                            CGB_STREAM_VEL_TRIAL);
+                const PairResult r = eval_pair(T, s_screen, w, cps, cvs, ces, &e_psi, &e_vesc, &e_env);
                 if (r.acc) t = 2ULL * mine + (unsigned)(r.acc - 1);
             }
             for (int o = 16; o; o >>= 1) {
@@ -905,7 +967,9 @@ __global__ void __launch_bounds__(512, 1) cgb_hard_kernel(SampleParams p)
     if (!s_last) return;
     __threadfence();
     for (unsigned h = threadIdx.x; h < n_hard; h += blockDim.x) {
-        const HardEntry e = ent[h];
+        const unsigned long long e_id = ent[h].id;
+        const double e_vesc = ent[h].vesc;
+        const long long loc = ent[h].loc;
         const unsigned long long best = *(volatile unsigned long long*)&ent[h].best;
         double v;
         int nt;
@@ -913,14 +977,11 @@ __global__ void __launch_bounds__(512, 1) cgb_hard_kernel(SampleParams p)
             v = __longlong_as_double(0x7ff8000000000000LL);
             nt = -1;
         } else {
-            const Philox4 w = philox4x32_10((unsigned)e.id, (unsigned)(e.id >> 32), (unsigned)(best >> 1),
-                                            CGB_STREAM_VEL_TRIAL, p.seed_lo, p.seed_hi);
-            const unsigned wa = (best & 1ULL) ? w.z : w.x;
-            const double vv = __dmul_rn(u32_to_double(wa) * 0x1.0p-32, e.vesc);
-            v = sqrt(__dmul_rn(vv, vv));
+            const Philox4 w = philox_rk(p.rk, (unsigned)e_id, (unsigned)(e_id >> 32), (unsigned)(best >> 1),
+                                        CGB_STREAM_VEL_TRIAL);
+            v = speed_of((best & 1ULL) ? w.z : w.x, e_vesc);
             nt = (int)min(best + 1ULL, 0x7fffffffULL);
         }
-        const long long loc = e.loc;
         if (MODE == 1) {
             p.speed[loc] = v;
             if (p.trials) p.trials[loc] = nt;
@@ -928,8 +989,7 @@ __global__ void __launch_bounds__(512, 1) cgb_hard_kernel(SampleParams p)
             double ucv, upv;
             if (HOST_U && p.hu.d_u_ctv) { ucv = p.hu.d_u_ctv[loc]; upv = p.hu.d_u_phv[loc]; }
             else {
-                const Philox4 w = philox4x32_10((unsigned)e.id, (unsigned)(e.id >> 32), 0u,
-                                                CGB_STREAM_VEL_DIR, p.seed_lo, p.seed_hi);
+                const Philox4 w = philox_rk(p.rk, (unsigned)e_id, (unsigned)(e_id >> 32), 0u, CGB_STREAM_VEL_DIR);
                 ucv = u52(w.x, w.y); upv = u52(w.z, w.w);
             }
             const double ctv = __dadd_rn(-1.0, __dmul_rn(2.0, ucv));
@@ -961,8 +1021,7 @@ __global__ void __launch_bounds__(512, 1) cgb_hard_kernel(SampleParams p)
 
 static size_t sample_smem_bytes()
 {
-    return NB * sizeof(float2) + (size_t)WARPS * 4 * (2 * TILE) * sizeof(double) +
-           (size_t)WARPS * CGB_NMOMENTS * sizeof(double);
+    return SCREEN_BYTES + (size_t)WARPS * (2 * TILE) * 32 + (size_t)WARPS * CGB_NMOMENTS * sizeof(double);
 }
 
 template <typename OutT, int MODE, bool HOST_U>
@@ -982,7 +1041,7 @@ static int launch_sample(const SampleParams& sp, cudaStream_t s)
     CGB_CUDA_CHECK(cudaMemsetAsync(sp.scratch, 0, sizeof(ScratchHeader), s));
     cgb_sample_kernel<OutT, MODE, HOST_U><<<(unsigned)ctas, WARPS * 32, smem, s>>>(sp);
     // grid-wide pass over the (rare) deferred particles; exits at once when there are none
-    cgb_hard_kernel<OutT, MODE, HOST_U><<<sms, 512, NB * sizeof(float2), s>>>(sp);
+    cgb_hard_kernel<OutT, MODE, HOST_U><<<sms, 512, SCREEN_BYTES, s>>>(sp);
     CGB_CUDA_CHECK(cudaGetLastError());
     return CGB_OK;
 }
@@ -1005,14 +1064,12 @@ __global__ void __launch_bounds__(256) cgb_gas_kernel(SampleParams p, void* aux0
         double u, uc, up;
         if (HOST_U && p.hu.d_u_r) u = p.hu.d_u_r[loc];
         else {
-            const Philox4 w = philox4x32_10((unsigned)id, (unsigned)(id >> 32), 0u, CGB_STREAM_RADIUS,
-                                            p.seed_lo, p.seed_hi);
+            const Philox4 w = philox_rk(p.rk, (unsigned)id, (unsigned)(id >> 32), 0u, CGB_STREAM_RADIUS);
             u = u52(w.x, w.y);
         }
         if (HOST_U && p.hu.d_u_ct) { uc = p.hu.d_u_ct[loc]; up = p.hu.d_u_ph[loc]; }
         else {
-            const Philox4 w = philox4x32_10((unsigned)id, (unsigned)(id >> 32), 0u, CGB_STREAM_POS_DIR,
-                                            p.seed_lo, p.seed_hi);
+            const Philox4 w = philox_rk(p.rk, (unsigned)id, (unsigned)(id >> 32), 0u, CGB_STREAM_POS_DIR);
             uc = u52(w.x, w.y); up = u52(w.z, w.w);
         }
         int lo = 0, hi = n_cdf - 1;
@@ -1057,14 +1114,12 @@ cgb_assemble_kernel(SampleParams p, const double* __restrict__ r_sub, const doub
         double uc, up, ucv, upv;
         if (HOST_U && p.hu.d_u_ct) { uc = p.hu.d_u_ct[loc]; up = p.hu.d_u_ph[loc]; }
         else {
-            const Philox4 w = philox4x32_10((unsigned)id, (unsigned)(id >> 32), 0u, CGB_STREAM_POS_DIR,
-                                            p.seed_lo, p.seed_hi);
+            const Philox4 w = philox_rk(p.rk, (unsigned)id, (unsigned)(id >> 32), 0u, CGB_STREAM_POS_DIR);
             uc = u52(w.x, w.y); up = u52(w.z, w.w);
         }
         if (HOST_U && p.hu.d_u_ctv) { ucv = p.hu.d_u_ctv[loc]; upv = p.hu.d_u_phv[loc]; }
         else {
-            const Philox4 w = philox4x32_10((unsigned)id, (unsigned)(id >> 32), 0u, CGB_STREAM_VEL_DIR,
-                                            p.seed_lo, p.seed_hi);
+            const Philox4 w = philox_rk(p.rk, (unsigned)id, (unsigned)(id >> 32), 0u, CGB_STREAM_VEL_DIR);
             ucv = u52(w.x, w.y); upv = u52(w.z, w.w);
         }
         const double ct = __dadd_rn(-1.0, __dmul_rn(2.0, uc));
@@ -1155,6 +1210,15 @@ extern "C" int cgb_sampler_prepare(const cgb_sampler_desc* desc, void* d_workspa
     return CGB_OK;
 }
 
+static void set_round_keys(SampleParams& sp, uint64_t seed)
+{
+    unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        sp.rk[2 * r] = k0; sp.rk[2 * r + 1] = k1;
+        k0 += CGB_PHILOX_W0; k1 += CGB_PHILOX_W1;
+    }
+}
+
 static int fill_params(const cgb_sample_args* a, SampleParams& sp, const char* who, bool need_vel)
 {
     CGB_REQUIRE(a != nullptr, "%s: null args", who);
@@ -1174,7 +1238,7 @@ static int fill_params(const cgb_sample_args* a, SampleParams& sp, const char* w
     sp.base = (const double*)a->d_workspace;
     sp.id_begin = a->id_begin; sp.id_end = a->id_end;
     sp.particle_mass = a->particle_mass;
-    sp.seed_lo = (unsigned)a->seed; sp.seed_hi = (unsigned)(a->seed >> 32);
+    set_round_keys(sp, a->seed);
     sp.pos = a->d_pos; sp.vel = a->d_vel; sp.ld = a->ld; sp.mass = a->d_mass; sp.pot = a->d_pot;
     sp.radius = a->d_radius; sp.speed = a->d_speed; sp.trials = a->d_trials; sp.moments = a->d_moments;
     sp.hu = a->hu;
@@ -1330,7 +1394,7 @@ extern "C" int cgb_generate_velocities(const double* d_psi, const double* d_vesc
     memset(&sp, 0, sizeof(sp));
     sp.base = (const double*)d_work;
     sp.id_begin = 0; sp.id_end = n; sp.first_id = first_id;
-    sp.seed_lo = (unsigned)seed; sp.seed_hi = (unsigned)(seed >> 32);
+    set_round_keys(sp, seed);
     sp.speed = d_vel; sp.trials = d_trials;
     sp.in_psi = d_psi; sp.in_vesc = d_vesc; sp.in_env = d_fv2esc;
     sp.hu.d_u_trial = d_u_trial; sp.hu.t_cap = t_cap;

@@ -30,4 +30,6 @@ for i in range(10):
     mom.zero_(); e0.record(); run(10 + i); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
 m = mom.cpu().numpy()
 ts.sort()
+hc = tabs.scratch[:16].cpu().numpy().view("uint32")
+print(f"hard_count {hc[2]} tiles {hc[0]}", end="  ")
 print(f"{name}/{ptype} n={n:.0e} median {ts[len(ts)//2]:.3f} ms  min {ts[0]:.3f} ms  {n/ts[len(ts)//2]/1e6:.2f} G particles/s  Tbar {m[1]/m[0]:.2f} coop {m[12]:.0f} exact/trial {m[15]/m[1]:.2e}")

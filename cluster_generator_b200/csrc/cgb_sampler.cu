@@ -491,11 +491,15 @@ __device__ __forceinline__ void store_out(void* p, long long i, double v)
     ((OutT*)p)[i] = (OutT)v;
 }
 
-// speed from the accepted first uniform: v = u1 * vesc, returned as sqrt(v^2) like the oracle
+// speed from the accepted first uniform: v = u1 * vesc.  The oracle returns sqrt(v*v);
+// in IEEE binary64 round-to-nearest sqrt(fl(v*v)) == |v| exactly whenever v*v neither
+// overflows nor underflows (v is a speed in kpc/Myr, O(1)), so the sqrt is only kept for
+// the out-of-range case.
 __device__ __forceinline__ double speed_of(unsigned wa, double vesc)
 {
     const double v = __dmul_rn(u32_to_double(wa) * 0x1.0p-32, vesc);
-    return sqrt(__dmul_rn(v, v));
+    const double v2 = __dmul_rn(v, v);
+    return (v2 > 1.0e-280 && v2 < 1.0e280) ? fabs(v) : sqrt(v2);
 }
 
 // MODE 0: fused DM/star sampler.  MODE 1: velocity-only (Cython seam mirror).
@@ -721,7 +725,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
             Philox4 w0, w1;
             w0.x = w0.y = w0.z = w0.w = 0;
             w1 = w0;
-            if (mine1 <= 0xFFFFFFFFull) {
+            // the first step looks at 32 pairs only: most stragglers need just a few more
+            const bool two = pr != p0;
+            if (two && mine1 <= 0xFFFFFFFFull) {
                 w0 = philox_rk(p.rk, cid_lo, cid_hi, (unsigned)mine0, CGB_STREAM_VEL_TRIAL);
                 w1 = philox_rk(p.rk, cid_lo, cid_hi, (unsigned)mine1, CGB_STREAM_VEL_TRIAL);
                 r0 = eval_pair(T, s_screen, w0, cps, cvs, ces, s_psi + s, s_ves + s, penv);
@@ -743,7 +749,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
                 }
                 break;
             }
-            pr += 64;
+            pr += two ? 64 : 32;
             if (pr >= HARD_PAIRS && !no_defer) {
                 // long tail: hand the particle to the grid-wide pass (cgb_hard_kernel)
                 unsigned h = 0;

@@ -1056,13 +1056,15 @@ static int launch_sample(const SampleParams& sp, cudaStream_t s)
 // gas / tracer kernel and the sub_sample assembly kernel (elementwise, HBM-bound)
 // ---------------------------------------------------------------------------
 template <typename OutT, bool HOST_U>
-__global__ void __launch_bounds__(256) cgb_gas_kernel(SampleParams p, void* aux0, void* aux1)
+__global__ void __launch_bounds__(256) cgb_gas_kernel(const __grid_constant__ SampleParams p, void* aux0, void* aux1)
 {
     const SamplerHeader* hdr = (const SamplerHeader*)p.base;
     const double* cdf_P = p.base + hdr->off_cdf_P;
     const double* cdf_r = p.base + hdr->off_cdf_r;
     const double* cdf_s = p.base + hdr->off_cdf_s;
-    const int n_cdf = hdr->n_cdf, npi = hdr->n_psi - 3, nai = hdr->n_aux_coef - 3;
+    const unsigned* cdf_lut = (const unsigned*)(p.base + hdr->off_cdf_lut);
+    const int2* cdf_iv = (const int2*)(p.base + hdr->off_cdf_iv);
+    const int npi = hdr->n_psi - 3, nai = hdr->n_aux_coef - 3;
     const long long n_local = p.id_end - p.id_begin;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long loc = (long long)blockIdx.x * blockDim.x + threadIdx.x; loc < n_local; loc += stride) {
@@ -1078,13 +1080,16 @@ __global__ void __launch_bounds__(256) cgb_gas_kernel(SampleParams p, void* aux0
             const Philox4 w = philox_rk(p.rk, (unsigned)id, (unsigned)(id >> 32), 0u, CGB_STREAM_POS_DIR);
             uc = u52(w.x, w.y); up = u52(w.z, w.w);
         }
-        int lo = 0, hi = n_cdf - 1;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (__ldg(cdf_P + mid) <= u) lo = mid; else hi = mid;
+        // bucket table + short search for np.interp's interval (same rule as the DM sampler)
+        const unsigned lh = __ldg(cdf_lut + cdf_bucket(u));
+        int lo = (int)(lh & 0xffffu), hi = (int)(lh >> 16);
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (__ldg(cdf_P + mid) <= u) lo = mid; else hi = mid - 1;
         }
         const double r = __dadd_rn(__dmul_rn(__ldg(cdf_s + lo), __dsub_rn(u, __ldg(cdf_P + lo))),
                                    __ldg(cdf_r + lo));
+        const int iv = __ldg(cdf_iv + lo).x;  // starting piece for every spline over `radius`
         const double ct = __dadd_rn(-1.0, __dmul_rn(2.0, uc));
         const double st = sqrt(__dmul_rn(__dsub_rn(1.0, ct), __dadd_rn(1.0, ct)));
         double sp, cp;
@@ -1099,9 +1104,18 @@ __global__ void __launch_bounds__(256) cgb_gas_kernel(SampleParams p, void* aux0
             store_out<OutT>(p.vel, 2 * p.ld + loc, 0.0);
         }
         if (p.mass) store_out<OutT>(p.mass, loc, p.particle_mass);
-        if (aux0) store_out<OutT>(aux0, loc, pp_eval(p.base + hdr->off_aux_brk[0], p.base + hdr->off_aux_pp[0], nai, r));
-        if (aux1) store_out<OutT>(aux1, loc, pp_eval(p.base + hdr->off_aux_brk[1], p.base + hdr->off_aux_pp[1], nai, r));
-        if (p.pot) store_out<OutT>(p.pot, loc, -pp_eval(p.base + hdr->off_psi_brk, p.base + hdr->off_psi_pp, npi, r));
+        if (aux0) {
+            const double* brk = p.base + hdr->off_aux_brk[0];
+            store_out<OutT>(aux0, loc, pp_eval_at(brk, p.base + hdr->off_aux_pp[0], pp_walk(brk, nai, iv, r), r));
+        }
+        if (aux1) {
+            const double* brk = p.base + hdr->off_aux_brk[1];
+            store_out<OutT>(aux1, loc, pp_eval_at(brk, p.base + hdr->off_aux_pp[1], pp_walk(brk, nai, iv, r), r));
+        }
+        if (p.pot) {
+            const double* brk = p.base + hdr->off_psi_brk;
+            store_out<OutT>(p.pot, loc, -pp_eval_at(brk, p.base + hdr->off_psi_pp, pp_walk(brk, npi, iv, r), r));
+        }
         if (p.radius) p.radius[loc] = r;
     }
 }

@@ -7,8 +7,16 @@ inverse-CDF radii, rejection-sampled speeds, behind the reference's own API
 The numerics are hand-written sm_100a CUDA reached through the C ABI in
 ``include/cgb200.h``; there is no CPU fallback.
 """
+from .ics import ClusterICs, compute_centers_for_binary  # noqa: F401
 from .model import ClusterModel  # noqa: F401
-from .particles import ClusterParticles  # noqa: F401
+from .particles import (  # noqa: F401
+    ClusterParticles,
+    combine_three_clusters,
+    combine_two_clusters,
+    resample_one_cluster,
+    resample_three_clusters,
+    resample_two_clusters,
+)
 from .radial_profiles import (  # noqa: F401
     RadialProfile,
     hernquist_density_profile,

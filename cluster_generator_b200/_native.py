@@ -58,6 +58,13 @@ class SampleArgs(Structure):
     ]
 
 
+class HaloTables(Structure):
+    _fields_ = [
+        ("d_dens_pp", c_void_p), ("d_ener_pp", c_void_p), ("n", c_int32), ("pad", c_int32),
+        ("center", c_double * 3), ("velocity", c_double * 3), ("radius_cut", c_double),
+    ]
+
+
 # every symbol include/cgb200.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ("cgb_version", c_int, []),
@@ -85,6 +92,10 @@ SYMBOLS = [
                                         c_int, c_void_p, c_int64, c_uint64, c_int64, c_void_p,
                                         c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
     ("cgb_sample_gas", c_int, [POINTER(SampleArgs), c_void_p, c_void_p, c_void_p]),
+    ("cgb_ppform_workspace_bytes", c_size_t, [c_int]),
+    ("cgb_ppform_prepare", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    ("cgb_resample_gas", c_int, [POINTER(HaloTables), c_int, c_void_p, c_int64, c_int64, c_int, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
 ]
 
 _LIB = None

@@ -1,0 +1,144 @@
+// Multi-halo gas re-sampling  -- replaces cluster_generator.particles._sample_clusters
+// (particles.py:587-639), the numeric part of combine_two/three_clusters and
+// resample_one/two/three_clusters (particles.py:642-795).
+//
+// For every gas particle: distance to each halo centre, density and thermal energy of
+// each halo's radial profile at that distance (cubic interpolating splines of
+// (radius, density) and (radius, 1.5 P / density), extrapolating like FITPACK ext=0),
+// then total density, mass-weighted specific energy and mass-weighted bulk velocity.
+// Elementwise, one thread per particle: 24 B read + 40 B written per particle.
+#include <math.h>
+#include "cgb_common.cuh"
+#include "cgb_spline.cuh"
+
+#define MAX_HALOS 3
+
+struct HaloDev {
+    const double* dens;  // pp workspace: brk[n-2 padded to 32] then pp[4 (n-3)]
+    const double* ener;
+    int n;
+    double cx, cy, cz, vx, vy, vz, rcut;
+};
+
+struct ResampleParams {
+    HaloDev h[MAX_HALOS];
+    int num_halos, use_radii, resample_mass;
+    const void* pos; long long ld; long long n;
+    void* density; void* thermal; void* vel; void* mass;
+};
+
+__device__ __forceinline__ int rs_find(const double* __restrict__ brk, int nint, double x)
+{
+    int lo = 0, hi = nint;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(brk + mid) <= x) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ double rs_eval(const double* __restrict__ ws, int n, int j, double x)
+{
+    const long long off = ((long long)(n - 2) + 31) / 32 * 32;
+    const double dx = x - __ldg(ws + j);
+    const double* pp = ws + off + 4 * (long long)j;
+    const double2 a01 = __ldg((const double2*)pp), a23 = __ldg((const double2*)pp + 1);
+    return fma(fma(fma(a23.y, dx, a23.x), dx, a01.y), dx, a01.x);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) cgb_resample_kernel(const __grid_constant__ ResampleParams p)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const T* pos = (const T*)p.pos;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
+        const double x = (double)pos[i], y = (double)pos[p.ld + i], z = (double)pos[2 * p.ld + i];
+        double dsum = 0.0, esum = 0.0, mx = 0.0, my = 0.0, mz = 0.0;
+        bool inside = (p.use_radii == 0);
+#pragma unroll
+        for (int k = 0; k < MAX_HALOS; ++k) {
+            if (k >= p.num_halos) break;
+            const HaloDev& h = p.h[k];
+            // r = sqrt(((pos - c)**2).sum(axis=1))                       (particles.py:594-596)
+            const double dx = __dsub_rn(x, h.cx), dy = __dsub_rn(y, h.cy), dz = __dsub_rn(z, h.cz);
+            const double r = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+            if (p.use_radii && r <= h.rcut) inside = true;
+            if (h.dens == nullptr) continue;          // halo without gas (particles.py:611-613)
+            const int j = rs_find(h.dens, h.n - 3, r);  // both splines share the radius knots
+            const double d = rs_eval(h.dens, h.n, j, r);
+            const double e = __dmul_rn(rs_eval(h.ener, h.n, j, r), d);
+            dsum = __dadd_rn(dsum, d);
+            esum = __dadd_rn(esum, e);
+            mx = __dadd_rn(mx, __dmul_rn(h.vx, d));
+            my = __dadd_rn(my, __dmul_rn(h.vy, d));
+            mz = __dadd_rn(mz, __dmul_rn(h.vz, d));
+        }
+        if (!inside) continue;
+        if (p.resample_mass) {
+            // vol = mass / density(old); mass = dens * vol                (particles.py:626-628)
+            T* m = (T*)p.mass;
+            const double vol = (double)m[i] / (double)((const T*)p.density)[i];
+            m[i] = (T)__dmul_rn(dsum, vol);
+        }
+        ((T*)p.density)[i] = (T)dsum;
+        ((T*)p.thermal)[i] = (T)(esum / dsum);
+        T* v = (T*)p.vel;
+        v[i] = (T)(mx / dsum);
+        v[p.ld + i] = (T)(my / dsum);
+        v[2 * p.ld + i] = (T)(mz / dsum);
+    }
+}
+
+extern "C" size_t cgb_ppform_workspace_bytes(int n)
+{
+    if (n < 4) return 0;
+    return (size_t)(((long long)(n - 2) + 31) / 32 * 32 + 4LL * (n - 3)) * sizeof(double);
+}
+
+extern "C" int cgb_ppform_prepare(const double* d_t, const double* d_c, int n, void* d_workspace,
+                                  size_t workspace_bytes, void* stream)
+{
+    CGB_REQUIRE(n >= 4 && d_t && d_c && d_workspace, "cgb_ppform_prepare: bad arguments");
+    if (workspace_bytes < cgb_ppform_workspace_bytes(n) || ((uintptr_t)d_workspace & 15)) {
+        cgb_set_error("cgb_ppform_prepare: workspace %zu B (need %zu, 16-byte aligned)", workspace_bytes,
+                      cgb_ppform_workspace_bytes(n));
+        return CGB_E_WORKSPACE;
+    }
+    double* ws = (double*)d_workspace;
+    return cgb_launch_pp_convert(d_t, d_c, n, ws, ws + ((long long)(n - 2) + 31) / 32 * 32, (cudaStream_t)stream);
+}
+
+extern "C" int cgb_resample_gas(const cgb_halo_tables* halos, int num_halos, const void* d_pos, int64_t ld,
+                                int64_t n, int dtype, void* d_density, void* d_thermal, void* d_vel,
+                                void* d_mass, int use_radii, void* stream)
+{
+    CGB_REQUIRE(halos != nullptr && num_halos >= 1 && num_halos <= MAX_HALOS,
+                "cgb_resample_gas: num_halos must be 1..3, got %d", num_halos);
+    CGB_REQUIRE(dtype == CGB_DTYPE_F64 || dtype == CGB_DTYPE_F32, "cgb_resample_gas: bad dtype %d", dtype);
+    CGB_REQUIRE(n >= 0 && ld >= n, "cgb_resample_gas: bad sizes");
+    if (n == 0) return CGB_OK;
+    CGB_REQUIRE(d_pos && d_density && d_thermal && d_vel, "cgb_resample_gas: null pointer");
+    ResampleParams p;
+    memset(&p, 0, sizeof(p));
+    bool any = false;
+    for (int k = 0; k < num_halos; ++k) {
+        const cgb_halo_tables& h = halos[k];
+        CGB_REQUIRE((h.d_dens_pp == nullptr) == (h.d_ener_pp == nullptr),
+                    "cgb_resample_gas: halo %d needs both density and energy tables", k);
+        if (h.d_dens_pp) CGB_REQUIRE(h.n >= 4, "cgb_resample_gas: halo %d has %d radial points", k, h.n);
+        any = any || h.d_dens_pp;
+        p.h[k].dens = h.d_dens_pp; p.h[k].ener = h.d_ener_pp; p.h[k].n = h.n;
+        p.h[k].cx = h.center[0]; p.h[k].cy = h.center[1]; p.h[k].cz = h.center[2];
+        p.h[k].vx = h.velocity[0]; p.h[k].vy = h.velocity[1]; p.h[k].vz = h.velocity[2];
+        p.h[k].rcut = h.radius_cut;
+    }
+    CGB_REQUIRE(any, "cgb_resample_gas: no halo carries a gas profile");
+    p.num_halos = num_halos; p.use_radii = use_radii; p.resample_mass = d_mass != nullptr;
+    p.pos = d_pos; p.ld = ld; p.n = n;
+    p.density = d_density; p.thermal = d_thermal; p.vel = d_vel; p.mass = d_mass;
+    const unsigned blocks = (unsigned)min((long long)((n + 255) / 256), 148LL * 16);
+    if (dtype == CGB_DTYPE_F64) cgb_resample_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    else cgb_resample_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    CGB_CUDA_CHECK(cudaGetLastError());
+    return CGB_OK;
+}

@@ -1,0 +1,124 @@
+"""
+Multi-halo initial conditions driver ("next" row 1 of SURVEY.md section 8(f)).
+
+Mirror of ``cluster_generator.ics.ClusterICs`` (ics.py:60-375) and
+``compute_centers_for_binary`` (ics.py:22-57) for the particle path: split the particle
+budget over halos by enclosed mass, generate DM / star / gas / tracer particles of every
+halo from ONE shared ``prng`` (stream order matters, ics.py:173-192), then offset and
+combine them, re-sampling the gas fields where halos overlap.
+
+Difference from the reference: ``profiles`` are :class:`ClusterModel` objects, not HDF5
+file names -- there is no HDF5 library in this environment, so the file round trip
+(``from_h5_file`` / ``write_particles``) is out of scope and nothing is written to disk.
+"""
+from __future__ import annotations
+
+from collections import defaultdict
+from numbers import Number
+
+import numpy as np
+
+from .particles import combine_three_clusters, combine_two_clusters
+from .utils import ensure_list, parse_prng
+
+
+def compute_centers_for_binary(center, d, b, a=0.0):
+    """Centres of two clusters a distance d apart with impact parameters b (y) and a (z)
+    around a common centre (ics.py:22-57)."""
+    d = np.sqrt(d * d - b * b - a * a)
+    diff = np.array([d, b, a])
+    center1 = center - 0.5 * diff
+    center2 = center + 0.5 * diff
+    return center1, center2
+
+
+class ClusterICs:
+    def __init__(self, basename, num_halos, profiles, center, velocity, num_particles=None,
+                 mag_file=None, particle_files=None, r_max=20000.0, r_max_tracer=None):
+        self.basename = basename
+        self.num_halos = int(num_halos)
+        if not 1 <= self.num_halos <= 3:
+            raise ValueError("num_halos must be 1, 2 or 3")
+        self.profiles = ensure_list(profiles)
+        if len(self.profiles) != self.num_halos:
+            raise ValueError("one profile (ClusterModel) per halo is required")
+        if any(isinstance(p, (str, bytes)) for p in self.profiles):
+            raise NotImplementedError(
+                "profile files need HDF5, which is not available here: pass ClusterModel objects")
+        if particle_files is not None:
+            raise NotImplementedError("particle files need HDF5, which is not available here")
+        self.center = np.asarray(center, dtype=np.float64).reshape(self.num_halos, 3)
+        self.velocity = np.asarray(velocity, dtype=np.float64).reshape(self.num_halos, 3)
+        self.mag_file = mag_file
+        if isinstance(r_max, Number):
+            r_max = [r_max] * self.num_halos
+        self.r_max = np.array(r_max)
+        if r_max_tracer is None:
+            r_max_tracer = r_max
+        if isinstance(r_max_tracer, Number):
+            r_max_tracer = [r_max_tracer] * self.num_halos
+        self.r_max_tracer = np.array(r_max_tracer)
+        self.tot_np = num_particles if num_particles is not None else {"dm": 0, "gas": 0, "star": 0, "tracer": 0}
+        self._determine_num_particles()
+
+    def _determine_num_particles(self):
+        """n_i = rint(N_tot * M_i(<r_max) / sum M) per species (ics.py:100-160)."""
+        dm_masses, gas_masses, star_masses, tracer_masses = [], [], [], []
+        for i, p in enumerate(self.profiles):
+            idxs = p["radius"].d < self.r_max[i]
+            dm_masses.append(p["dark_matter_mass"].d[idxs][-1])
+            gas_masses.append(p["gas_mass"].d[idxs][-1] if "gas_mass" in p else 0.0)
+            star_masses.append(p["stellar_mass"].d[idxs][-1] if "stellar_mass" in p else 0.0)
+            if self.tot_np.get("tracer", 0) > 0:
+                idxst = p["radius"].d < self.r_max_tracer[i]
+                tracer_masses.append(p["gas_mass"].d[idxst][-1])
+            else:
+                tracer_masses.append(0.0)
+        totals = {"dm": np.sum(dm_masses), "gas": np.sum(gas_masses), "star": np.sum(star_masses),
+                  "tracer": np.sum(tracer_masses)}
+        masses = {"dm": dm_masses, "gas": gas_masses, "star": star_masses, "tracer": tracer_masses}
+        self.num_particles = defaultdict(list)
+        for i in range(self.num_halos):
+            for key in ("dm", "gas", "star", "tracer"):
+                if self.tot_np.get(key, 0) > 0:
+                    n = int(np.rint(self.tot_np[key] * masses[key][i] / totals[key]))
+                else:
+                    n = 0
+                self.num_particles[key].append(n)
+
+    def _generate_particles(self, output_directory=None, regenerate_particles=False, prng=None, **kw):
+        """ics.py:162-200: dm -> star -> gas -> tracer per halo, one shared prng."""
+        prng = parse_prng(prng)
+        parts = []
+        for i, m in enumerate(self.profiles):
+            p = m.generate_dm_particles(self.num_particles["dm"][i], r_max=self.r_max[i], prng=prng, **kw)
+            if self.num_particles["star"][i] > 0:
+                p = p + m.generate_star_particles(self.num_particles["star"][i], r_max=self.r_max[i],
+                                                  prng=prng, **kw)
+            if self.num_particles["gas"][i] > 0:
+                p = p + m.generate_gas_particles(self.num_particles["gas"][i], r_max=self.r_max[i],
+                                                 prng=prng, **kw)
+            if self.num_particles["tracer"][i] > 0:
+                p = p + m.generate_tracer_particles(self.num_particles["tracer"][i],
+                                                    r_max=self.r_max_tracer[i], prng=prng, **kw)
+            parts.append(p)
+        return parts
+
+    def setup_particle_ics(self, output_directory=None, regenerate_particles=False, prng=None, **kw):
+        """Generate and combine the particles of all halos (ics.py:323-375)."""
+        profiles = self.profiles
+        parts = self._generate_particles(output_directory=output_directory,
+                                         regenerate_particles=regenerate_particles, prng=prng, **kw)
+        if self.num_halos == 1:
+            all_parts = parts[0]
+            all_parts.add_offsets(self.center[0], self.velocity[0])
+        elif self.num_halos == 2:
+            all_parts = combine_two_clusters(parts[0], parts[1], profiles[0], profiles[1],
+                                             self.center[0], self.center[1], self.velocity[0],
+                                             self.velocity[1])
+        else:
+            all_parts = combine_three_clusters(parts[0], parts[1], parts[2], profiles[0], profiles[1],
+                                               profiles[2], self.center[0], self.center[1],
+                                               self.center[2], self.velocity[0], self.velocity[1],
+                                               self.velocity[2])
+        return all_parts

@@ -102,3 +102,115 @@ class ClusterParticles:
     def to_numpy(self):
         """Host copy: dict (ptype, field) -> ndarray."""
         return {k: v.detach().cpu().numpy() for k, v in self.fields.items()}
+
+
+# --------------------------------------------------------------------------- #
+# multi-halo combination / gas re-sampling (particles.py:587-795)
+# --------------------------------------------------------------------------- #
+def _planes(t: torch.Tensor) -> torch.Tensor:
+    """(n, 3) field -> its contiguous (3, n) plane storage (copying only if it has none)."""
+    p = t.T
+    return p if p.is_contiguous() else p.contiguous()
+
+
+def _sample_clusters(particles, hses, center, velocity, radii=None, resample=False, passive_scalars=None):
+    """Re-sample the gas fields from the overlap of up to three radial profiles
+    (particles.py:587-639): total density, mass-weighted specific thermal energy and
+    mass-weighted bulk velocity at every gas particle.  Runs in ``cgb_resample_gas``."""
+    import numpy as np
+
+    from . import _native as N
+    from .virial import DeviceSpline
+
+    if passive_scalars:
+        raise NotImplementedError("passive scalars are outside the particle-sampling path")
+    num_halos = len(hses)
+    if not 1 <= num_halos <= 3:
+        raise ValueError("between one and three halos are supported")
+    n = particles.num_particles["gas"]
+    pos = _planes(particles["gas", "particle_position"])
+    vel = _planes(particles["gas", "particle_velocity"])
+    dens, therm = particles["gas", "density"], particles["gas", "thermal_energy"]
+    mass = particles["gas", "particle_mass"]
+    dtype = pos.dtype
+    code = N.CGB_DTYPE_F64 if dtype == torch.float64 else N.CGB_DTYPE_F32
+    for t in (vel, dens, therm, mass):
+        if t.dtype != dtype or not t.is_contiguous():
+            raise ValueError("gas fields must share one dtype and be contiguous")
+    L = N.lib()
+    keep = []
+    halos = (N.HaloTables * num_halos)()
+    for i, hse in enumerate(hses):
+        c = np.asarray(center[i], dtype=np.float64).reshape(3)
+        v = np.asarray(velocity[i], dtype=np.float64).reshape(3)
+        halos[i].center[:] = c.tolist()
+        halos[i].velocity[:] = v.tolist()
+        halos[i].radius_cut = float(radii[i]) if radii is not None else -1.0
+        if "density" not in hse:
+            continue  # halo without gas (particles.py:611-613)
+        rr = np.asarray(hse["radius"], dtype=np.float64)
+        rho = np.asarray(hse["density"], dtype=np.float64)
+        e_arr = 1.5 * np.asarray(hse["pressure"], dtype=np.float64) / rho
+        halos[i].n = rr.size
+        for name, y in (("d_dens_pp", rho), ("d_ener_pp", e_arr)):
+            s = DeviceSpline.fit(rr, y)
+            nb = L.cgb_ppform_workspace_bytes(s.n)
+            ws = N.workspace(nb)
+            N.check(L.cgb_ppform_prepare(N.ptr(s.t), N.ptr(s.c), s.n, N.ptr(ws), nb, N.stream_ptr()))
+            keep.append((s, ws))
+            setattr(halos[i], name, ws.data_ptr())
+    N.check(L.cgb_resample_gas(halos, num_halos, N.ptr(pos), n, n, code, N.ptr(dens), N.ptr(therm),
+                               N.ptr(vel), N.ptr(mass) if resample else None,
+                               1 if radii is not None else 0, N.stream_ptr()))
+    particles.fields["gas", "particle_velocity"] = vel.T
+    del keep
+    return particles
+
+
+def _combine(parts, hses, centers, velocities):
+    """combine_two_clusters / combine_three_clusters (particles.py:642-715): gas is offset in
+    position only, the collisionless species in position and velocity; the gas fields are
+    then re-sampled from the overlapping profiles."""
+    for p, c, v in zip(parts, centers, velocities):
+        if "gas" in p.particle_types:
+            p.add_offsets(c, [0.0] * 3, ptypes=["gas"])
+        others = [t for t in p.particle_types if t != "gas"]
+        p.add_offsets(c, v, ptypes=others)
+    particles = parts[0]
+    for p in parts[1:]:
+        particles = particles + p
+    if "gas" in particles.particle_types:
+        particles = _sample_clusters(particles, hses, centers, velocities)
+    return particles
+
+
+def combine_two_clusters(particles1, particles2, hse1, hse2, center1, center2, velocity1, velocity2):
+    """particles.py:642-666"""
+    return _combine([particles1, particles2], [hse1, hse2], [center1, center2], [velocity1, velocity2])
+
+
+def combine_three_clusters(particles1, particles2, particles3, hse1, hse2, hse3, center1, center2,
+                           center3, velocity1, velocity2, velocity3):
+    """particles.py:669-715"""
+    return _combine([particles1, particles2, particles3], [hse1, hse2, hse3],
+                    [center1, center2, center3], [velocity1, velocity2, velocity3])
+
+
+def resample_one_cluster(particles, hse, center, velocity):
+    """particles.py:718-744"""
+    if "gas" not in particles.particle_types:
+        return particles
+    return _sample_clusters(particles, [hse], [center], [velocity], resample=True)
+
+
+def resample_two_clusters(particles, hse1, hse2, center1, center2, velocity1, velocity2, radii):
+    """particles.py:747-768"""
+    return _sample_clusters(particles, [hse1, hse2], [center1, center2], [velocity1, velocity2],
+                            radii=radii, resample=True)
+
+
+def resample_three_clusters(particles, hse1, hse2, hse3, center1, center2, center3, velocity1,
+                            velocity2, velocity3, radii):
+    """particles.py:771-795"""
+    return _sample_clusters(particles, [hse1, hse2, hse3], [center1, center2, center3],
+                            [velocity1, velocity2, velocity3], radii=radii, resample=True)

@@ -233,6 +233,34 @@ int cgb_generate_velocities(const double *d_psi, const double *d_vesc, const dou
  * d_aux_out[k]: nullable f64/f32 arrays (out_dtype) for aux spline k. */
 int cgb_sample_gas(const cgb_sample_args *args, void *d_aux_out0, void *d_aux_out1, void *stream);
 
+/* ------------------------------------------------------------------------ */
+/* Multi-halo gas re-sampling ("next" row 1 of SURVEY.md section 8(f))        */
+/*   replaces _sample_clusters (particles.py:587-639), the numeric part of    */
+/*   combine_two/three_clusters and resample_*_clusters (particles.py:642-795) */
+/* ------------------------------------------------------------------------ */
+/* Piecewise-polynomial form of a FITPACK cubic spline (knots d_t[n+4], coefficients
+ * d_c[n]) in caller memory; what cgb_resample_gas evaluates. */
+size_t cgb_ppform_workspace_bytes(int n);
+int cgb_ppform_prepare(const double *d_t, const double *d_c, int n, void *d_workspace,
+                       size_t workspace_bytes, void *stream);
+
+typedef struct cgb_halo_tables {
+    const double *d_dens_pp; /* ppform of IUS(radius, density)            (particles.py:615) */
+    const double *d_ener_pp; /* ppform of IUS(radius, 1.5 pressure/density) (particles.py:617-618) */
+    int32_t n;               /* radial points of both splines; NULL tables = halo without gas */
+    int32_t pad;
+    double center[3];        /* kpc     */
+    double velocity[3];      /* kpc/Myr */
+    double radius_cut;       /* radii[i] of the resample mask (particles.py:597-601) */
+} cgb_halo_tables;
+
+/* halos: HOST array of num_halos (1..3) entries.  d_pos / d_vel: (3, ld) planes; d_density,
+ * d_thermal: (n,) in/out; d_mass: NULL, or the particle masses to rescale (resample=True);
+ * use_radii != 0: only particles within radius_cut of at least one centre are updated. */
+int cgb_resample_gas(const cgb_halo_tables *halos, int num_halos, const void *d_pos, int64_t ld,
+                     int64_t n, int dtype, void *d_density, void *d_thermal, void *d_vel,
+                     void *d_mass, int use_radii, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

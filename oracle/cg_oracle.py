@@ -455,6 +455,70 @@ def generate_gas_particles(model, num_particles, r_max=None, sub_sample=1,
 
 
 # --------------------------------------------------------------------------- #
+# Multi-halo combination (particles.py:587-715, ics.py:22-57) on dict-of-ndarray particles
+# --------------------------------------------------------------------------- #
+def compute_centers_for_binary(center, d, b, a=0.0):
+    """ics.py:22-57"""
+    d = np.sqrt(d * d - b * b - a * a)
+    diff = np.array([d, b, a])
+    return center - 0.5 * diff, center + 0.5 * diff
+
+
+def sample_clusters(fields, hses, center, velocity, radii=None, resample=False):
+    """particles.py:587-639 (without passive scalars); ``fields`` is updated in place."""
+    num_halos = len(hses)
+    pos = fields["gas", "particle_position"]
+    n = pos.shape[0]
+    r = np.zeros((num_halos, n))
+    for i, c in enumerate(center):
+        r[i, :] = ((pos - np.asarray(c)) ** 2).sum(axis=1)
+    np.sqrt(r, r)
+    if radii is None:
+        idxs = slice(None, None, None)
+    else:
+        radii = np.array(radii)
+        idxs = np.any(r <= radii[:, np.newaxis], axis=0)
+    d = np.zeros((num_halos, n))
+    e = np.zeros((num_halos, n))
+    m = np.zeros((num_halos, 3, n))
+    for i, hse in enumerate(hses):
+        if "density" not in hse:
+            continue
+        get_density = InterpolatedUnivariateSpline(hse["radius"], hse["density"])
+        d[i, :] = get_density(r[i, :])
+        e_arr = 1.5 * hse["pressure"] / hse["density"]
+        get_energy = InterpolatedUnivariateSpline(hse["radius"], e_arr)
+        e[i, :] = get_energy(r[i, :]) * d[i, :]
+        m[i, :, :] = np.asarray(velocity[i])[:, np.newaxis] * d[i, :]
+    dens = d.sum(axis=0)
+    eint = e.sum(axis=0) / dens
+    mom = m.sum(axis=0) / dens
+    if resample:
+        vol = fields["gas", "particle_mass"] / fields["gas", "density"]
+        fields["gas", "particle_mass"][idxs] = dens[idxs] * vol[idxs]
+    fields["gas", "density"][idxs] = dens[idxs]
+    fields["gas", "thermal_energy"][idxs] = eint[idxs]
+    fields["gas", "particle_velocity"][idxs] = mom.T[idxs]
+    return fields
+
+
+def combine_clusters(parts, hses, centers, velocities):
+    """particles.py:642-715: ``parts`` = list of field dicts, one per halo."""
+    out = OrderedDict()
+    for f, c, v in zip(parts, centers, velocities):
+        for (pt, name), arr in f.items():
+            arr = np.array(arr, dtype=np.float64)
+            if name == "particle_position":
+                arr = arr + np.asarray(c)
+            elif name == "particle_velocity" and pt != "gas":
+                arr = arr + np.asarray(v)
+            out[pt, name] = arr if (pt, name) not in out else np.concatenate([out[pt, name], arr])
+    if any(k[0] == "gas" for k in out):
+        sample_clusters(out, hses, centers, velocities)
+    return out
+
+
+# --------------------------------------------------------------------------- #
 # Row V: the rejection loop (C restatement in oracle/cg_oracle_c.c)
 # --------------------------------------------------------------------------- #
 _HERE = os.path.dirname(os.path.abspath(__file__))

@@ -539,3 +539,73 @@ def test_device_qags_matches_scipy_traces_decision_for_decision():
         np.testing.assert_array_equal(o[54:54 + L], ref[3 + L:3 + 2 * L], err_msg=key)       # blist
         np.testing.assert_allclose(o[104:104 + L], ref[3 + 2 * L:3 + 3 * L], rtol=1e-13, atol=1e-300, err_msg=key)
         np.testing.assert_allclose(o[0], ref[0], rtol=1e-13, err_msg=key)
+
+
+# --------------------------------------------------------------------------- #
+# "next" row 1: multi-halo ICs (ics.py, particles.py:587-715)
+# --------------------------------------------------------------------------- #
+def _oracle_halo(oracle, om, n_dm, n_gas, seed, r_max):
+    u = oracle.device_rng_uniforms(seed, 0, n_dm)
+    dm = om.dm_virial.generate_particles(
+        n_dm, r_max=r_max, uniforms=u,
+        velocity_fn=lambda *a: oracle.generate_velocities_counter(*a, seed=seed))
+    gas = oracle.generate_gas_particles(om, n_gas, r_max=r_max, uniforms=oracle.device_rng_uniforms(seed + 1, 0, n_gas))
+    f = dict(dm)
+    f.update(gas)
+    return f
+
+
+def test_two_cluster_ics_match_oracle(oracle):
+    """BASELINE config 4 shape at test size: binary merger, d = 3000, b = 500, v = +-500
+    (tests/test_ics.py:94-96), gas re-sampled from both profiles."""
+    import cluster_generator_b200 as cg
+    import cluster_generator_b200.model as M
+    import cluster_generator_b200.virial as V
+
+    om, pm = oracle_model("vikhlinin"), product_model("vikhlinin")
+    c1, c2 = cg.compute_centers_for_binary(np.array([7000.0, 7000.0, 7000.0]), 3000.0, 500.0)
+    v1, v2 = np.array([500.0, 0.0, 0.0]), np.array([-500.0, 0.0, 0.0])
+    ics = cg.ClusterICs("t", 2, [pm, pm], [c1, c2], [v1, v2],
+                        num_particles={"dm": 60_000, "gas": 60_000}, r_max=5000.0)
+    assert ics.num_particles["dm"] == [30_000, 30_000] and ics.num_particles["gas"] == [30_000, 30_000]
+    seeds = iter([101, 102, 201, 202])          # dm0, gas0, dm1, gas1 in the driver's call order
+    orig_v, orig_m = V.seed_from_prng, M.seed_from_prng
+    V.seed_from_prng = M.seed_from_prng = lambda prng, species: next(seeds)
+    try:
+        allp = ics.setup_particle_ics(prng=0)
+    finally:
+        V.seed_from_prng, M.seed_from_prng = orig_v, orig_m
+    h0 = _oracle_halo(oracle, om, 30_000, 30_000, 101, 5000.0)
+    h1 = _oracle_halo(oracle, om, 30_000, 30_000, 201, 5000.0)
+    ref = oracle.combine_clusters([h0, h1], [om, om], [c1, c2], [v1, v2])
+    assert allp.num_particles == {"dm": 60_000, "gas": 60_000}
+    for key in (("dm", "particle_position"), ("gas", "particle_position")):
+        np.testing.assert_allclose(_np(allp[key]), ref[key], rtol=1e-10, atol=1e-8)
+    np.testing.assert_allclose(_np(allp["dm", "particle_velocity"]), ref["dm", "particle_velocity"], rtol=1e-10, atol=1e-10)
+    for f in ("density", "thermal_energy"):
+        np.testing.assert_allclose(_np(allp["gas", f]), ref["gas", f], rtol=1e-8, err_msg=f)
+    np.testing.assert_allclose(_np(allp["gas", "particle_velocity"]), ref["gas", "particle_velocity"], rtol=1e-8, atol=1e-9)
+    # the overlap really changes things: densities exceed the single-halo profile somewhere
+    assert (ref["gas", "density"] > 0).all()
+    vx = _np(allp["gas", "particle_velocity"])[:, 0]
+    assert vx.min() < -400 and vx.max() > 400 and np.abs(vx).min() < 50
+
+
+def test_resample_with_radii_matches_oracle(oracle):
+    import cluster_generator_b200 as cg
+
+    om, pm = oracle_model("vikhlinin"), product_model("vikhlinin")
+    n = 40_000
+    p = pm.generate_gas_particles(n, prng=5)
+    fields = {k: _np(v).copy() for k, v in p.fields.items()}
+    c1, c2 = np.zeros(3), np.array([1500.0, 200.0, 0.0])
+    v1, v2 = np.array([1.0, 0.0, 0.0]), np.array([-2.0, 0.5, 0.0])
+    radii = [800.0, 600.0]
+    ref = oracle.sample_clusters(fields, [om, om], [c1, c2], [v1, v2], radii=radii, resample=True)
+    out = cg.resample_two_clusters(p, pm, pm, c1, c2, v1, v2, radii)
+    for f in ("density", "thermal_energy", "particle_mass"):
+        np.testing.assert_allclose(_np(out["gas", f]), ref["gas", f], rtol=1e-8, err_msg=f)
+    np.testing.assert_allclose(_np(out["gas", "particle_velocity"]), ref["gas", "particle_velocity"], rtol=1e-8, atol=1e-12)
+    untouched = np.linalg.norm(fields["gas", "particle_position"] - c1, axis=1) > 800.0
+    untouched &= np.linalg.norm(fields["gas", "particle_position"] - c2, axis=1) > 600.0
+    assert untouched.any() and not _np(out["gas", "particle_velocity"])[untouched].any()

@@ -232,3 +232,39 @@ def test_moments_all_reduce_two_ranks_gloo(tmp_path):
     d = torch.load(out)
     assert d["particles"] == n and d["sum_trials"] == sum(range(n)) and d["max_trials"] == 11.0
     assert d["mean_trials"] == pytest.approx(sum(range(n)) / n)
+
+
+def test_compute_centers_for_binary_known_answer():
+    """cluster_generator/tests/test_ics.py:160-173"""
+    import cluster_generator_b200 as cg
+    from oracle import cg_oracle as O
+
+    for fn in (cg.compute_centers_for_binary, O.compute_centers_for_binary):
+        c1, c2 = fn(np.array([0.0, 0.0, 0.0]), 3000.0, 500.0)
+        sep = np.sqrt(3000.0**2 - 500.0**2)
+        np.testing.assert_allclose(c1, [-0.5 * sep, -250.0, 0.0])
+        np.testing.assert_allclose(c2, [0.5 * sep, 250.0, 0.0])
+        assert np.linalg.norm(c2 - c1) == pytest.approx(3000.0)
+        c1, c2 = fn(np.array([1.0, 2.0, 3.0]), 1000.0, 300.0, a=400.0)
+        assert np.linalg.norm(c2 - c1) == pytest.approx(1000.0)
+
+
+def test_cluster_ics_particle_budget_split():
+    """ics.py:100-160: n_i = rint(N * M_i / sum M) per species; 1:3 mass ratio (config 4)."""
+    import cluster_generator_b200 as cg
+    from tests.configs import product_model
+
+    big = product_model("hernquist")                       # M = 1e15
+    fields = {k: np.array(v) for k, v in big.fields.items()}
+    for k in ("total_mass", "dark_matter_mass", "total_density", "dark_matter_density",
+              "gravitational_potential", "gravitational_field"):
+        fields[k] = fields[k] / 3.0
+    small = cg.ClusterModel.from_arrays(fields)
+    ics = cg.ClusterICs("m", 2, [big, small], [[0, 0, 0], [3000, 0, 0]], [[0, 0, 0], [0, 0, 0]],
+                        num_particles={"dm": 1_000_000}, r_max=5000.0)
+    assert ics.num_particles["dm"] == [750_000, 250_000]
+    assert ics.num_particles["gas"] == [0, 0] and ics.num_particles["star"] == [0, 0]
+    with pytest.raises(NotImplementedError):
+        cg.ClusterICs("m", 1, ["model.h5"], [0, 0, 0], [0, 0, 0])
+    with pytest.raises(ValueError):
+        cg.ClusterICs("m", 2, [big], [[0, 0, 0]] * 2, [[0, 0, 0]] * 2)

@@ -35,6 +35,7 @@ METRIC = "particles/sec (pos+vel, device-timed)"
 UNIT = "particles/s"
 F_FIXED, F_TRIAL = 200.0, 52.0   # algorithmic flop per DM particle = 200 + 52 * T
 B_DM, B_GAS = 56.0, 72.0         # algorithmic bytes written per particle (fp64)
+NCU_DRAM_BYTES_PER_LAUNCH = 515.6e6  # 1.9 MB read + 513.7 MB written (algorithmic: 560 MB, part still in L2)
 
 
 def build_product_model():
@@ -353,7 +354,9 @@ def run_cuda(args):
         "kernel": "cgb_sample_kernel<double,0,false>",
         "bound": "fp64_pipe" if t_pipe >= t_hbm else "hbm",
         "achieved": ach_tflops, "peak": dfma.value, "unit": "TFLOP/s", "frac": ach_tflops / dfma.value,
-        "traffic": None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this
+        # workload, from the ncu --set full capture summarised in profiles/r01_ncu_full_summary.md
+        "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
         "peak_source": "DFMA microbenchmark measured live (cgb_measure_dfma_tflops); MEASURED_PEAKS.json has no FP64 figure",
         "algorithmic_flops_per_particle": flops_per_particle, "mean_trials": tbar,
         "kernel_ms": k_ms, "dm_particles_per_s_kernel": n / k_s,

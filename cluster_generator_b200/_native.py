@@ -80,6 +80,8 @@ SYMBOLS = [
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     ("cgb_check_virial", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p]),
+    ("cgb_integrate_spline", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_double,
+                                     c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
     ("cgb_qags_trace", c_int, [c_void_p, c_void_p, c_int, c_double, c_double, c_double, c_double,
                                c_double, c_int, c_void_p, c_void_p]),
     ("cgb_sampler_workspace_bytes", c_size_t, [POINTER(SamplerDesc)]),
@@ -164,7 +166,10 @@ def dev_f64(a, device=None) -> torch.Tensor:
     device = device or require_cuda()
     if isinstance(a, torch.Tensor):
         return a.to(device=device, dtype=torch.float64).contiguous()
-    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(device)
+    arr = np.ascontiguousarray(a, dtype=np.float64)
+    if not arr.flags.writeable:
+        arr = arr.copy()
+    return torch.from_numpy(arr).to(device)
 
 
 def workspace(nbytes: int, device=None) -> torch.Tensor:

@@ -84,6 +84,21 @@ __device__ __forceinline__ double pow15(double x)
     return hi + lo;
 }
 
+// model.py:219-224 / utils.py:137-142:  profile(r) = spline(r) * r**power, the integrand of
+// the potential table (power 1) and of spline-tabulated mass integrals (power 2)
+struct PowSplineIntegrand {
+    const double* t;
+    const double* c;
+    int nk;
+    int power;
+    __device__ __forceinline__ double operator()(double x) const
+    {
+        double v = cgb_splev(t, nk, c, x);
+        for (int k = 0; k < power; ++k) v = v * x;
+        return v;
+    }
+};
+
 // Warp-cooperative dqk21.  All lanes return identical values.
 template <class F>
 __device__ __forceinline__ void dqk21_warp(const F& f, double a, double b, double& result,
@@ -547,6 +562,36 @@ cgb_check_virial_kernel(const double* __restrict__ ee, const double* __restrict_
     }
 }
 
+// out[i] = quad(lambda x: s(x) * x**power, a[i], b[i], epsabs, epsrel)[0]
+__global__ void __launch_bounds__(EDD_WARPS * 32)
+cgb_integrate_spline_kernel(const double* __restrict__ t, const double* __restrict__ c, int n,
+                            const double* __restrict__ a, const double* __restrict__ b, int m, int power,
+                            double epsabs, double epsrel, double* __restrict__ out,
+                            int* __restrict__ last_out, int* __restrict__ ier_out)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int nk = n + 4;
+    double* s_t = (double*)smem;
+    double* s_c = s_t + nk;
+    QagsScratch* scr = (QagsScratch*)(s_c + n);
+    for (int i = threadIdx.x; i < nk; i += blockDim.x) s_t[i] = t[i];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s_c[i] = c[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bin = blockIdx.x * EDD_WARPS + warp;
+    if (bin >= m) return;
+    PowSplineIntegrand f;
+    f.t = s_t; f.c = s_c; f.nk = nk; f.power = power;
+    double result, abserr;
+    int last;
+    const int ier = dqagse_warp(f, a[bin], b[bin], epsabs, epsrel, QAGS_LIMIT, scr[warp], result, abserr, last);
+    if (lane == 0) {
+        out[bin] = result;
+        if (last_out) last_out[bin] = last;
+        if (ier_out) ier_out[bin] = ier;
+    }
+}
+
 // ff = g'(ee) / (sqrt(8) pi^2)                                       (virial.py:66)
 __global__ void cgb_ff_kernel(const double* __restrict__ t, const double* __restrict__ wrk, int n,
                               const double* __restrict__ ee, double inv_norm_den,
@@ -675,6 +720,25 @@ extern "C" int cgb_eddington_df(const double* d_ee, const double* d_pden, int n,
     CGB_CUDA_CHECK(cudaGetLastError());
     // self.f = IUS(ee, ff)                                            (virial.py:67)
     if ((rc = cgb_launch_spline_fit(d_ee, d_ff, n, d_f_t, d_f_c, fit_scratch, s))) return rc;
+    return CGB_OK;
+}
+
+extern "C" int cgb_integrate_spline(const double* d_t, const double* d_c, int n, const double* d_a,
+                                    const double* d_b, int m, int power, double epsabs, double epsrel,
+                                    double* d_out, int* d_last, int* d_ier, void* stream)
+{
+    CGB_REQUIRE(n >= 4 && d_t && d_c, "cgb_integrate_spline: bad spline");
+    CGB_REQUIRE(power >= 0 && power <= 4, "cgb_integrate_spline: power must be 0..4, got %d", power);
+    CGB_REQUIRE(m >= 0, "cgb_integrate_spline: negative count");
+    if (m == 0) return CGB_OK;
+    CGB_REQUIRE(d_a && d_b && d_out, "cgb_integrate_spline: null pointer");
+    const size_t smem = edd_smem_bytes(n);
+    CGB_REQUIRE(smem <= 227 * 1024, "cgb_integrate_spline: n = %d needs %zu B of shared memory", n, smem);
+    CGB_CUDA_CHECK(cudaFuncSetAttribute(cgb_integrate_spline_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cgb_integrate_spline_kernel<<<(m + EDD_WARPS - 1) / EDD_WARPS, EDD_WARPS * 32, smem, (cudaStream_t)stream>>>(
+        d_t, d_c, n, d_a, d_b, m, power, epsabs, epsrel, d_out, d_last, d_ier);
+    CGB_CUDA_CHECK(cudaGetLastError());
     return CGB_OK;
 }
 

@@ -75,14 +75,22 @@ class ClusterModel:
         return cls(np.asarray(fields["radius"]).size, OrderedDict(fields))
 
     @classmethod
-    def _from_scratch(cls, fields, stellar_density=None):
-        """model.py:213-269"""
+    def _from_scratch(cls, fields, stellar_density=None, integrator="host"):
+        """model.py:213-269.  ``integrator="device"`` runs the N potential integrals
+        (utils.py:137-142, ~1 s of host ``quad`` calls) on the GPU instead."""
+        if integrator not in ("host", "device"):
+            raise ValueError("integrator must be 'host' or 'device'")
         rr = np.asarray(fields["radius"])
         mylog.info("Integrating gravitational potential profile.")
         tdens_func = InterpolatedUnivariateSpline(rr, fields["total_density"])
         gpot_profile = lambda r: tdens_func(r) * r
         gpot1 = fields["total_mass"] / fields["radius"]
-        gpot2 = 4.0 * np.pi * integrate(gpot_profile, rr)
+        if integrator == "device":
+            from .utils import integrate_spline_device
+
+            gpot2 = 4.0 * np.pi * integrate_spline_device(tdens_func, rr, np.full_like(rr, rr[-1]), power=1)
+        else:
+            gpot2 = 4.0 * np.pi * integrate(gpot_profile, rr)
         fields["gravitational_potential"] = -G * (gpot1 + gpot2)
 
         if "density" in fields and "gas_mass" not in fields:
@@ -117,7 +125,7 @@ class ClusterModel:
         return cls(rr.size, fields)
 
     @classmethod
-    def no_gas(cls, rmin, rmax, total_density, stellar_density=None, num_points=1000):
+    def no_gas(cls, rmin, rmax, total_density, stellar_density=None, num_points=1000, integrator="host"):
         """Model without a gas component (model.py:620-656)."""
         rr = np.logspace(np.log10(rmin), np.log10(rmax), num_points, endpoint=True)
         fields = OrderedDict()
@@ -126,10 +134,11 @@ class ClusterModel:
         mylog.info("Integrating total mass profile.")
         fields["total_mass"] = integrate_mass(total_density, rr)
         fields["gravitational_field"] = -G * fields["total_mass"] / (fields["radius"] ** 2)
-        return cls._from_scratch(fields, stellar_density=stellar_density)
+        return cls._from_scratch(fields, stellar_density=stellar_density, integrator=integrator)
 
     @classmethod
-    def from_dens_and_temp(cls, rmin, rmax, density, temperature, stellar_density=None, num_points=1000):
+    def from_dens_and_temp(cls, rmin, rmax, density, temperature, stellar_density=None, num_points=1000,
+                           integrator="host"):
         """Hydrostatic model from gas density and temperature (model.py:474-523)."""
         mylog.info("Computing the profiles from density and temperature.")
         rr = np.logspace(np.log10(rmin), np.log10(rmax), num_points, endpoint=True)
@@ -148,7 +157,7 @@ class ClusterModel:
         total_mass_spline = InterpolatedUnivariateSpline(rr, fields["total_mass"])
         dMdr = total_mass_spline(rr, nu=1)
         fields["total_density"] = dMdr / (4.0 * np.pi * fields["radius"] ** 2)
-        return cls._from_scratch(fields, stellar_density=stellar_density)
+        return cls._from_scratch(fields, stellar_density=stellar_density, integrator=integrator)
 
     @classmethod
     def from_dens_and_tden(cls, rmin, rmax, density, total_density, stellar_density=None, num_points=1000):

@@ -110,3 +110,29 @@ def ensure_list(x):
     if isinstance(x, (list, tuple, set)):
         return list(x)
     return [x]
+
+
+def integrate_spline_device(spline, a, b, power=1, epsabs=1.49e-8, epsrel=1.49e-8):
+    """``[quad(lambda x: spline(x) * x**power, a_i, b_i)[0] for i]`` on the GPU.
+
+    ``spline`` is a scipy ``InterpolatedUnivariateSpline`` (its FITPACK knots and
+    coefficients are uploaded as they are, so the integrand is the reference's to the
+    bit); the quadrature is the same QUADPACK ``dqagse`` restatement that builds f(E).
+    Used for the potential table (model.py:219-224) when ``integrator="device"``.
+    """
+    import torch
+
+    from . import _native as N
+
+    t, c, k = spline._eval_args
+    if k != 3:
+        raise ValueError("cubic splines only")
+    a = np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), np.shape(b) or np.shape(a)))
+    b = np.ascontiguousarray(np.broadcast_to(np.asarray(b, dtype=np.float64), a.shape))
+    n = len(t) - 4
+    td, cd = N.dev_f64(t), N.dev_f64(np.asarray(c)[:n])
+    ad, bd = N.dev_f64(a), N.dev_f64(b)
+    out = torch.empty(a.size, dtype=torch.float64, device=td.device)
+    N.check(N.lib().cgb_integrate_spline(N.ptr(td), N.ptr(cd), n, N.ptr(ad), N.ptr(bd), a.size, int(power),
+                                         epsabs, epsrel, N.ptr(out), None, None, N.stream_ptr()))
+    return out.cpu().numpy().reshape(a.shape)

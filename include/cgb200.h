@@ -109,6 +109,15 @@ int cgb_check_virial(const double *d_ee, const double *d_pden, int n, const doub
                      const double *d_f_c, double *d_rho, double *d_chk, int *d_last, int *d_ier,
                      void *stream);
 
+/* T (next row 3): m QAGS integrals of spline(x) * x**power over [d_a[i], d_b[i]] with the
+ * spline given by FITPACK knots d_t[n+4] / coefficients d_c[n].
+ *   replaces utils.integrate (utils.py:137-142) for the potential table, whose integrand
+ *   is IUS(r, total_density)(r) * r  (model.py:219-224, power = 1), one quad per radius;
+ *   same decision-for-decision dqagse restatement as cgb_eddington_df. */
+int cgb_integrate_spline(const double *d_t, const double *d_c, int n, const double *d_a,
+                         const double *d_b, int m, int power, double epsabs, double epsrel,
+                         double *d_out, int *d_last, int *d_ier, void *stream);
+
 /* Diagnostic: ONE QAGS integral with its full adaptive state, so tests can compare
  * the device quadrature decision for decision with QUADPACK (scipy's
  * quad(..., full_output=1): last, alist, blist, rlist, elist).

@@ -609,3 +609,28 @@ def test_resample_with_radii_matches_oracle(oracle):
     untouched = np.linalg.norm(fields["gas", "particle_position"] - c1, axis=1) > 800.0
     untouched &= np.linalg.norm(fields["gas", "particle_position"] - c2, axis=1) > 600.0
     assert untouched.any() and not _np(out["gas", "particle_velocity"])[untouched].any()
+
+
+# --------------------------------------------------------------------------- #
+# "next" row 3: the potential table on the device (model.py:219-224, utils.py:137-142)
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("name", ["hernquist", "vikhlinin"])
+def test_device_potential_integral_matches_scipy(name):
+    import time
+
+    import cluster_generator_b200 as cg
+
+    om = oracle_model(name)
+    t0 = time.perf_counter()
+    if name == "hernquist":
+        pm = cg.ClusterModel.no_gas(0.1, 1.0e4, cg.hernquist_density_profile(1.0e15, 500.0), integrator="device")
+    else:
+        dens = cg.vikhlinin_density_profile(4.2e5, 100.0, 1000.0, 1.0, 0.67, 3.0)
+        temp = cg.vikhlinin_temperature_profile(10.0, 0.0, 2.0, 1.0, 1500.0, 6.0, 80.0, 1.0)
+        pm = cg.ClusterModel.from_dens_and_temp(0.1, 1.0e4, dens, temp, integrator="device")
+    print(name, "model build with device integrator:", time.perf_counter() - t0, "s")
+    phi, phi_o = np.asarray(pm["gravitational_potential"]), om["gravitational_potential"]
+    np.testing.assert_allclose(phi, phi_o, rtol=1e-12)
+    assert (phi == phi_o).mean() > 0.9            # same QUADPACK decisions: mostly bit-equal
+    with pytest.raises(ValueError):
+        cg.ClusterModel.no_gas(0.1, 1.0e4, cg.hernquist_density_profile(1.0e15, 500.0), integrator="gpu")

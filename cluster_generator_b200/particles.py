@@ -99,6 +99,49 @@ class ClusterParticles:
         self._update_num_particles()
         self._update_field_names()
 
+    def make_radial_cut(self, r_max, center=None, ptypes=None):
+        """Remove all particles outside ``r_max`` of ``center`` (particles.py:139-167)."""
+        rm2 = r_max * r_max
+        if ptypes is None:
+            ptypes = self.particle_types
+        for part in ensure_list(ptypes):
+            pos = self.fields[part, "particle_position"]
+            c = torch.as_tensor([0.0] * 3 if center is None else center, dtype=pos.dtype, device=pos.device)
+            cidx = ((pos - c) ** 2).sum(dim=1) <= rm2
+            for field in self.field_names[part]:
+                f = self.fields[part, field]
+                # keep the plane-major storage of the (n, 3) fields
+                self.fields[part, field] = f.T[:, cidx].contiguous().T if f.dim() == 2 else f[cidx]
+        self._update_num_particles()
+
+    def add_black_hole(self, bh_mass, pos=None, vel=None, use_pot_min=False):
+        """Add a black hole particle (particles.py:169-225)."""
+        ref = self.fields[self.particle_types[0], "particle_mass"]
+        kw = dict(dtype=ref.dtype, device=ref.device)
+        mass = torch.tensor([bh_mass], **kw)
+        if use_pot_min:
+            if ("dm", "potential_energy") not in self.fields:
+                raise KeyError("('dm', 'potential_energy') is not available!")
+            idx = int(torch.argmin(self.fields["dm", "potential_energy"]))
+            pos = self.fields["dm", "particle_position"][idx].reshape(1, 3).clone()
+            vel = self.fields["dm", "particle_velocity"][idx].reshape(1, 3).clone()
+        else:
+            pos = torch.zeros((1, 3), **kw) if pos is None else torch.as_tensor(pos, **kw).reshape(1, 3)
+            vel = torch.zeros((1, 3), **kw) if vel is None else torch.as_tensor(vel, **kw).reshape(1, 3)
+        if "black_hole" not in self.particle_types:
+            self.particle_types.append("black_hole")
+            self.fields["black_hole", "particle_position"] = pos
+            self.fields["black_hole", "particle_velocity"] = vel
+            self.fields["black_hole", "particle_mass"] = mass
+        else:
+            for name, new in (("particle_position", pos), ("particle_velocity", vel), ("particle_mass", mass)):
+                self.fields["black_hole", name] = torch.cat([self.fields["black_hole", name], new], dim=0)
+        for k in (("black_hole", "particle_position"), ("black_hole", "particle_velocity"),
+                  ("black_hole", "particle_mass")):
+            self.field_units.setdefault(k, FIELD_UNITS.get(k[1], ""))
+        self._update_num_particles()
+        self._update_field_names()
+
     def to_numpy(self):
         """Host copy: dict (ptype, field) -> ndarray."""
         return {k: v.detach().cpu().numpy() for k, v in self.fields.items()}

@@ -634,3 +634,37 @@ def test_device_potential_integral_matches_scipy(name):
     assert (phi == phi_o).mean() > 0.9            # same QUADPACK decisions: mostly bit-equal
     with pytest.raises(ValueError):
         cg.ClusterModel.no_gas(0.1, 1.0e4, cg.hernquist_density_profile(1.0e15, 500.0), integrator="gpu")
+
+
+# --------------------------------------------------------------------------- #
+# SURVEY.md section 8(d) config-2 hazard (i): strong cool core => f(E) < 0 in a band =>
+# non-positive envelopes whose accept test degenerates.  Reference behaviour, reproduced.
+# --------------------------------------------------------------------------- #
+def test_negative_distribution_function_band_is_reproduced(oracle):
+    import cluster_generator_b200 as cg
+    import cluster_generator_b200.virial as V
+
+    dens_o = oracle.vikhlinin_density_profile(4.2e5, 100.0, 1000.0, 1.0, 0.67, 3.0)
+    temp_o = oracle.vikhlinin_temperature_profile(10.0, 0.0, 2.0, 1.0, 1500.0, 4.0, 80.0, 1.5)
+    om = oracle.from_dens_and_temp(0.1, 1.0e4, dens_o, temp_o)
+    dens = cg.vikhlinin_density_profile(4.2e5, 100.0, 1000.0, 1.0, 0.67, 3.0)
+    temp = cg.vikhlinin_temperature_profile(10.0, 0.0, 2.0, 1.0, 1500.0, 4.0, 80.0, 1.5)
+    pm = cg.ClusterModel.from_dens_and_temp(0.1, 1.0e4, dens, temp)
+    ov, pv = om.dm_virial, pm.dm_virial
+    assert (ov.ff < 0).sum() > 10                                  # the band exists
+    np.testing.assert_allclose(pv.ff, ov.ff, rtol=1e-8, atol=1e-8 * np.abs(ov.ff).max() * 1e-6)
+    n, seed = 200_000, 31
+    f = ov.generate_particles(n, uniforms=oracle.device_rng_uniforms(seed, 0, n),
+                              velocity_fn=lambda *a: oracle.generate_velocities_counter(*a, seed=seed))
+    nonpos = int((ov.last["fv2esc"] <= 0).sum())
+    assert nonpos > 0
+    orig = V.seed_from_prng
+    V.seed_from_prng = lambda prng, species: seed
+    try:
+        p = pv.generate_particles(n, prng=0)
+    finally:
+        V.seed_from_prng = orig
+    d = p.diagnostics["dm"].as_dict()
+    assert d["nonpositive_envelopes"] == nonpos                     # counted and reported
+    assert d["sum_trials"] == ov.last_trials.sum() and d["max_trials"] == ov.last_trials.max()
+    _vec_close(_np(p["dm", "particle_velocity"]), f["dm", "particle_velocity"], RTOL64, ov.last["speed"])

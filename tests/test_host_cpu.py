@@ -168,6 +168,28 @@ def test_cluster_particles_container():
     assert allp.particle_types == ["dm"] and ("star", "particle_mass") not in allp
 
 
+def test_radial_cut_and_black_hole():
+    """particles.py:139-225 on CPU tensors."""
+    from cluster_generator_b200 import ClusterParticles
+
+    n = 100
+    g = torch.Generator().manual_seed(0)
+    pos = torch.rand((3, n), generator=g, dtype=torch.float64) * 200.0 - 100.0
+    p = ClusterParticles("dm", {("dm", "particle_position"): pos.T, ("dm", "particle_velocity"): (pos * 0.1).T,
+                                ("dm", "particle_mass"): torch.ones(n, dtype=torch.float64),
+                                ("dm", "potential_energy"): -torch.arange(n, dtype=torch.float64)})
+    keep = (pos**2).sum(dim=0) <= 80.0**2
+    p.make_radial_cut(80.0)
+    assert p.num_particles["dm"] == int(keep.sum()) and p["dm", "particle_position"].T.is_contiguous()
+    assert torch.equal(p["dm", "particle_position"], pos.T[keep])
+    p.add_black_hole(1.0e9)
+    p.add_black_hole(2.0e9, use_pot_min=True)
+    assert p.num_particles["black_hole"] == 2 and "black_hole" in p.particle_types
+    idx = int(torch.argmin(p["dm", "potential_energy"]))
+    assert torch.equal(p["black_hole", "particle_position"][1], p["dm", "particle_position"][idx])
+    assert p["black_hole", "particle_mass"].tolist() == [1.0e9, 2.0e9]
+
+
 def test_radial_profile_algebra():
     """cluster_generator/tests/test_radial_profiles.py:100-123"""
     import cluster_generator_b200 as cg

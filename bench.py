@@ -58,14 +58,52 @@ def build_oracle_model():
 # clocks during the timed region (B200_PROFILING.md recipe)
 # --------------------------------------------------------------------------- #
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: an NVML polling thread
+    (5 ms cadence, so even a 40 ms region gets samples); nvidia-smi is the fallback."""
+
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.gpu, self.proc, self.f = gpu_index, None, None
+        self.thread, self.stop_flag, self.samples, self.reasons, self.max_mhz = None, False, [], set(), None
+
+    def _poll(self):
+        import pynvml as nv
+
+        h = self.handle
+        bits = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            import threading
+
+            import pynvml as nv
+
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].isdigit() else self.gpu
+            self.handle = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.proc = subprocess.Popen(
@@ -76,6 +114,14 @@ class ClockSampler:
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            sm = sorted(float(x) for x in self.samples)
+            if sm:
+                out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=self.max_mhz, samples=len(sm), source="nvml 5 ms poll")
+            out["reasons"] = sorted(self.reasons)
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -102,10 +148,10 @@ class ClockSampler:
         os.unlink(self.f.name)
         if sm:
             sm.sort()
-            # median of the upper half = under load (idle samples before/after pull the median down)
             top = sm[len(sm) // 2:]
             out["sm_mhz"] = top[len(top) // 2]
             out["samples"] = len(sm)
+            out["source"] = "nvidia-smi 100 ms"
         out["reasons"] = sorted(reasons)
         return out
 
@@ -269,10 +315,9 @@ def run_cuda(args):
         step(i)
     barrier()
     clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-        time.sleep(0.15)
     barrier()
+    if rank == 0:
+        clocks.start()  # started right before the timed region: every sample is under load
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for i in range(args.steps):
@@ -400,7 +445,7 @@ def run_cuda(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     args = ap.parse_args()

@@ -36,8 +36,12 @@
 #define WARPS 16           // warps per CTA
 #endif
 #ifndef TILE
-#define TILE 128           // particles per warp tile buffer (two buffers per warp)
+#define TILE 128           // particles per warp tile buffer
 #endif
+#ifndef NBUF
+#define NBUF 2             // tile buffers per warp (ring): a straggler may keep its lane for
+#endif                     // NBUF-1 tile lifetimes before the warp has to finish it.  Measured
+                           // (1e7 Vikhlinin DM): 2x128 1.06 ms, 3x96 1.13, 4x64 1.15, 4x96 1.19
 #define NBC 1024           // buckets of the CDF start-index table
 #ifndef LANE_CAP_PAIRS
 #define LANE_CAP_PAIRS 96  // trial pairs a particle may spend in its lane before the warp takes over
@@ -520,14 +524,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
     float2* s_screen = (float2*)smem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // per-warp slot arrays, 2 buffers x TILE slots, 32 B per slot
-    unsigned char* wbase = smem + SCREEN_BYTES + (size_t)warp * (2 * TILE) * 32;
+    unsigned char* wbase = smem + SCREEN_BYTES + (size_t)warp * (NBUF * TILE) * 32;
     double* s_psi = (double*)wbase;            // relative potential
-    double* s_ves = s_psi + 2 * TILE;          // escape speed
-    double* s_rad = s_ves + 2 * TILE;          // radius (MODE 0)
-    float* s_es = (float*)(s_rad + 2 * TILE);  // fp32 envelope for the screen; trial count once done
-    unsigned* s_wa = (unsigned*)(s_es + 2 * TILE);  // accepted first uniform (32 bits)
+    double* s_ves = s_psi + NBUF * TILE;          // escape speed
+    double* s_rad = s_ves + NBUF * TILE;          // radius (MODE 0)
+    float* s_es = (float*)(s_rad + NBUF * TILE);  // fp32 envelope for the screen; trial count once done
+    unsigned* s_wa = (unsigned*)(s_es + NBUF * TILE);  // accepted first uniform (32 bits)
     int* s_tri = (int*)s_es;
-    double* s_mom = (double*)(smem + SCREEN_BYTES + (size_t)WARPS * (2 * TILE) * 32) + (size_t)warp * CGB_NMOMENTS;
+    double* s_mom = (double*)(smem + SCREEN_BYTES + (size_t)WARPS * (NBUF * TILE) * 32) + (size_t)warp * CGB_NMOMENTS;
     const unsigned FULL = 0xffffffffu;
     const unsigned lt_mask = (1u << lane) - 1u;
 
@@ -545,11 +549,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
     const long long id_base = (MODE == 0 ? p.id_begin : p.first_id);
     // warp-uniform buffer state
     // (scalars selected by ternaries: dynamically indexed arrays would go to local memory)
-    long long b_loc0_0 = 0, b_loc0_1 = 0;
-    int b_cnt_0 = 0, b_cnt_1 = 0, b_next_0 = 0, b_next_1 = 0, b_fin_0 = 0, b_fin_1 = 0;
-    bool b_live_0 = false, b_live_1 = false;
-#define BGET(name, b) ((b) ? name##_1 : name##_0)
-#define BSET(name, b, v) do { if (b) name##_1 = (v); else name##_0 = (v); } while (0)
+    // (read / written only through fully unrolled compare-selects so they stay in registers)
+    long long b_loc0[NBUF];
+    int b_cnt[NBUF], b_next[NBUF], b_fin[NBUF];
+    bool b_live[NBUF];
+#pragma unroll
+    for (int k = 0; k < NBUF; ++k) { b_loc0[k] = 0; b_cnt[k] = 0; b_next[k] = 0; b_fin[k] = 0; b_live[k] = false; }
+#define BGET(name, b) ([&]() { auto _v = name[0]; _Pragma("unroll") for (int _k = 1; _k < NBUF; ++_k) if ((b) == _k) _v = name[_k]; return _v; }())
+#define BSET(name, b, v) do { _Pragma("unroll") for (int _k = 0; _k < NBUF; ++_k) if ((b) == _k) name[_k] = (v); } while (0)
     bool more_tiles = true;
     int cur = 0;
 
@@ -776,7 +783,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
             }
         }
         ++m_coop;
-        if (s >= TILE) ++b_fin_1; else ++b_fin_0;
+        BSET(b_fin, s / TILE, BGET(b_fin, s / TILE) + 1);
         if (lane == src) slot = -1;
         __syncwarp();
     };
@@ -793,10 +800,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
     if (HOST_U && p.hu.d_u_trial) {
         // literal host-supplied (u1,u2)[t_cap] per particle: exact path only, tile by tile
         while (acquire(0)) {
-            for (int i = lane; i < b_cnt_0; i += 32) {
+            for (int i = lane; i < b_cnt[0]; i += 32) {
                 const double psi = s_psi[i], vesc = s_ves[i];
-                const double env = (MODE == 0) ? envelope_of(T, psi) : p.in_env[b_loc0_0 + i];
-                const double* uu = p.hu.d_u_trial + (size_t)(b_loc0_0 + i) * (size_t)p.hu.t_cap * 2;
+                const double env = (MODE == 0) ? envelope_of(T, psi) : p.in_env[b_loc0[0] + i];
+                const double* uu = p.hu.d_u_trial + (size_t)(b_loc0[0] + i) * (size_t)p.hu.t_cap * 2;
                 int acc = -1;
                 double v2 = 0.0;
                 for (long long t = 0; t < p.hu.t_cap; ++t) {
@@ -809,21 +816,39 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
             }
             epilogue(0);
         }
-    } else if (acquire(0)) {
+    } else {
+        // One call site each for acquire() and epilogue() (they are large and inlined): the
+        // loop is a small state machine.  `pending` = buffers whose tile is complete and
+        // must be written out; it starts the ring with cur = NBUF-1 empty so that the first
+        // refill acquires buffer 0.
+        unsigned pending = 0;
+        bool exiting = false;
+        cur = NBUF - 1;
         for (;;) {
+            while (pending) {
+                const int k = __ffs(pending) - 1;
+                pending &= pending - 1;
+                epilogue(k);
+            }
+            if (exiting) break;
             // ---- refill idle lanes from the current buffer, rolling to the next tile ----
             unsigned need = __ballot_sync(FULL, slot < 0);
+            bool restart = false;
             while (need) {
                 const int avail = BGET(b_cnt, cur) - BGET(b_next, cur);
                 if (avail == 0) {
                     if (!more_tiles) break;
-                    const int other = cur ^ 1;
-                    if (BGET(b_live, other)) {  // recycle: its stragglers are finished by the whole warp
-                        finish_lanes(__ballot_sync(FULL, slot >= 0 && slot / TILE == other));
-                        epilogue(other);
+                    const int nxt = (cur + 1) % NBUF;  // the oldest buffer of the ring
+                    if (BGET(b_live, nxt)) {
+                        // recycle: its stragglers are finished by the whole warp, then it is
+                        // written out at the top of the loop
+                        finish_lanes(__ballot_sync(FULL, slot >= 0 && slot / TILE == nxt));
+                        pending |= 1u << nxt;
+                        restart = true;
+                        break;
                     }
-                    if (!acquire(other)) break;
-                    cur = other;
+                    if (!acquire(nxt)) break;
+                    cur = nxt;
                     need = __ballot_sync(FULL, slot < 0);
                     continue;
                 }
@@ -843,11 +868,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
                 if (want <= avail) break;
                 need = __ballot_sync(FULL, slot < 0);
             }
+            if (restart) continue;
             const unsigned act = __ballot_sync(FULL, slot >= 0);
-            if (act == 0) break;
-            if (!more_tiles && BGET(b_next, cur) == BGET(b_cnt, cur)) {
-                finish_lanes(act);  // nothing left to claim anywhere: final drain
-                break;
+            if (act == 0 || (!more_tiles && BGET(b_next, cur) == BGET(b_cnt, cur))) {
+                // nothing left to claim anywhere: final drain, then write out what is held
+                if (act) finish_lanes(act);
+#pragma unroll
+                for (int k = 0; k < NBUF; ++k)
+                    if (b_live[k]) pending |= 1u << k;
+                exiting = true;
+                continue;
             }
             // ---- one Philox call = two trials for every active lane ----
             bool done = false;
@@ -867,20 +897,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
             // long runners leave their lane: the warp finishes them 128 trials at a time
             const unsigned lng = __ballot_sync(FULL, slot >= 0 && !done && pair >= LANE_CAP_PAIRS);
             if (lng) finish_lanes(lng);
-            if (__any_sync(FULL, done)) {
-                const unsigned d0 = __ballot_sync(FULL, done && slot < TILE);
-                const unsigned d1 = __ballot_sync(FULL, done && slot >= TILE);
+            if (lng || __any_sync(FULL, done)) {
+                const int myb = done ? slot / TILE : -1;
                 if (done) slot = -1;
-                b_fin_0 += __popc(d0);
-                b_fin_1 += __popc(d1);
-                // a fully finished tile that is no longer being claimed from goes out
-                const int other = cur ^ 1;
-                if (BGET(b_live, other) && BGET(b_fin, other) == BGET(b_cnt, other)) epilogue(other);
+#pragma unroll
+                for (int k = 0; k < NBUF; ++k) {
+                    b_fin[k] += __popc(__ballot_sync(FULL, myb == k));
+                    // a fully finished tile that is no longer being claimed from goes out
+                    if (k != cur && b_live[k] && b_fin[k] == b_cnt[k]) pending |= 1u << k;
+                }
             }
         }
-        // write out whatever is still held
-        if (BGET(b_live, cur ^ 1)) epilogue(cur ^ 1);
-        if (BGET(b_live, cur)) epilogue(cur);
     }
 
     // ---------------- moments ----------------
@@ -1027,7 +1054,7 @@ __global__ void __launch_bounds__(512, 1) cgb_hard_kernel(const __grid_constant_
 
 static size_t sample_smem_bytes()
 {
-    return SCREEN_BYTES + (size_t)WARPS * (2 * TILE) * 32 + (size_t)WARPS * CGB_NMOMENTS * sizeof(double);
+    return SCREEN_BYTES + (size_t)WARPS * (NBUF * TILE) * 32 + (size_t)WARPS * CGB_NMOMENTS * sizeof(double);
 }
 
 template <typename OutT, int MODE, bool HOST_U>

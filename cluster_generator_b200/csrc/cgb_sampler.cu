@@ -616,7 +616,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
         const long long id0 = id_base + loc0;
         double a_v2 = 0.0, a_psi = 0.0, a_r = 0.0, a_px = 0.0, a_py = 0.0, a_pz = 0.0, a_vx = 0.0,
                a_vy = 0.0, a_vz = 0.0;
-        unsigned a_tr = 0, a_tmax = 0, a_fail = 0;
+        unsigned long long a_tr = 0;  // 64-bit: a single long-tail particle can need > 2^31 trials
+        unsigned a_tmax = 0, a_fail = 0;
         __syncwarp();
         for (int i = lane; i < cnt; i += 32) {
             const int s = b * TILE + i;
@@ -685,7 +686,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
                 for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
                 return x;
             };
-            const unsigned tr = __reduce_add_sync(FULL, a_tr);
+            unsigned long long tr = a_tr;
+            for (int o = 16; o; o >>= 1) tr += __shfl_xor_sync(FULL, tr, o);
             const unsigned tm = __reduce_max_sync(FULL, a_tmax);
             const unsigned fl = __reduce_add_sync(FULL, a_fail);
             a_v2 = wsum(a_v2); a_psi = wsum(a_psi); a_r = wsum(a_r);

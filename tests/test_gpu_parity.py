@@ -668,3 +668,35 @@ def test_negative_distribution_function_band_is_reproduced(oracle):
     assert d["nonpositive_envelopes"] == nonpos                     # counted and reported
     assert d["sum_trials"] == ov.last_trials.sum() and d["max_trials"] == ov.last_trials.max()
     _vec_close(_np(p["dm", "particle_velocity"]), f["dm", "particle_velocity"], RTOL64, ov.last["speed"])
+
+
+def test_full_size_properties_config3_headline():
+    """BASELINE config 3 (headline): NFW DM + Hernquist BCG stars, 1e8 particles split by
+    enclosed mass like ClusterICs (ics.py:132-153), here on one GPU.  Size-independent
+    properties only (the oracle would need ~10 CPU-minutes for this)."""
+    import cluster_generator_b200 as cg
+
+    pm = product_model("nfw_bcg")
+    ics = cg.ClusterICs("c3", 1, [pm], [0.0, 0.0, 0.0], [0.0, 0.0, 0.0],
+                        num_particles={"dm": 99_000_000, "star": 1_000_000}, r_max=1.0e4)
+    assert ics.num_particles["dm"] == [99_000_000] and ics.num_particles["star"] == [1_000_000]
+    p = ics.setup_particle_ics(prng=11, compute_potential=False)
+    assert p.num_particles == {"dm": 99_000_000, "star": 1_000_000}
+    for pt, lo, hi in (("dm", 15.0, 40.0), ("star", 150.0, 600.0)):      # SURVEY section 6 T-bar: 23 / 293
+        d = p.diagnostics[pt].as_dict()
+        assert d["failures"] == 0 and lo < d["mean_trials"] < hi, (pt, d["mean_trials"])
+        pos, vel = p[pt, "particle_position"], p[pt, "particle_velocity"]
+        assert torch.isfinite(pos).all() and torch.isfinite(vel).all()
+        r = torch.linalg.norm(pos, dim=1)
+        assert float(r.max()) < 1.0e4 * (1 + 1e-12)
+        # isotropy of both vectors: |<cos theta>| within 5 sigma
+        n = pos.shape[0]
+        assert abs(float((pos[:, 2] / r).mean())) < 5.0 / (3.0 * n) ** 0.5
+        v = torch.linalg.norm(vel, dim=1)
+        assert abs(float((vel[:, 2] / v).mean())) < 5.0 / (3.0 * n) ** 0.5
+        # moments reported by the kernel agree with the data it wrote
+        np.testing.assert_allclose(d["sum_v2"], float((v.double() ** 2).sum()), rtol=1e-9)
+        np.testing.assert_allclose(d["sum_r"], float(r.double().sum()), rtol=1e-9)
+    # stars are more concentrated than the dark matter
+    assert float(torch.linalg.norm(p["star", "particle_position"], dim=1).median()) < \
+        0.2 * float(torch.linalg.norm(p["dm", "particle_position"], dim=1).median())

@@ -522,7 +522,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
 {
     extern __shared__ __align__(16) unsigned char smem[];
     float2* s_screen = (float2*)smem;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // opaque to the compiler, otherwise it re-reads SR_TID.X (a slow S2R) all over the loop
+    asm volatile("" : "+r"(warp), "+r"(lane));
     // per-warp slot arrays, 2 buffers x TILE slots, 32 B per slot
     unsigned char* wbase = smem + SCREEN_BYTES + (size_t)warp * (NBUF * TILE) * 32;
     double* s_psi = (double*)wbase;            // relative potential

@@ -54,7 +54,7 @@ class SampleArgs(Structure):
         ("particle_mass", c_double), ("seed", c_uint64), ("out_dtype", c_int32), ("flags", c_int32),
         ("d_pos", c_void_p), ("d_vel", c_void_p), ("ld", c_int64), ("d_mass", c_void_p),
         ("d_pot", c_void_p), ("d_radius", c_void_p), ("d_speed", c_void_p), ("d_trials", c_void_p),
-        ("d_moments", c_void_p), ("hu", HostUniforms),
+        ("d_moments", c_void_p), ("hu", HostUniforms), ("radius_period", c_int64),
     ]
 
 

@@ -332,6 +332,7 @@ struct SampleParams {
     // velocity-only mode (cgb_generate_velocities): per-particle inputs
     const double* in_psi; const double* in_vesc; const double* in_env;
     long long first_id;
+    long long radius_period;  // gas sub_sample: radius of id taken from id % radius_period
 };
 
 // Philox4x32-10 with the key schedule taken from the kernel parameters
@@ -1100,10 +1101,12 @@ __global__ void __launch_bounds__(256) cgb_gas_kernel(const __grid_constant__ Sa
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long loc = (long long)blockIdx.x * blockDim.x + threadIdx.x; loc < n_local; loc += stride) {
         const unsigned long long id = (unsigned long long)(p.id_begin + loc);
+        // sub_sample: np.tile(radius_sub, s)[:n]                       (model.py:887-890)
+        const unsigned long long rid = p.radius_period > 0 ? id % (unsigned long long)p.radius_period : id;
         double u, uc, up;
-        if (HOST_U && p.hu.d_u_r) u = p.hu.d_u_r[loc];
+        if (HOST_U && p.hu.d_u_r) u = p.hu.d_u_r[p.radius_period > 0 ? (long long)rid : loc];
         else {
-            const Philox4 w = philox_rk(p.rk, (unsigned)id, (unsigned)(id >> 32), 0u, CGB_STREAM_RADIUS);
+            const Philox4 w = philox_rk(p.rk, (unsigned)rid, (unsigned)(rid >> 32), 0u, CGB_STREAM_RADIUS);
             u = u52(w.x, w.y);
         }
         if (HOST_U && p.hu.d_u_ct) { uc = p.hu.d_u_ct[loc]; up = p.hu.d_u_ph[loc]; }
@@ -1293,6 +1296,8 @@ static int fill_params(const cgb_sample_args* a, SampleParams& sp, const char* w
     sp.pos = a->d_pos; sp.vel = a->d_vel; sp.ld = a->ld; sp.mass = a->d_mass; sp.pot = a->d_pot;
     sp.radius = a->d_radius; sp.speed = a->d_speed; sp.trials = a->d_trials; sp.moments = a->d_moments;
     sp.hu = a->hu;
+    sp.radius_period = a->radius_period;
+    CGB_REQUIRE(a->radius_period >= 0, "%s: negative radius_period", who);
     return CGB_OK;
 }
 

@@ -259,8 +259,6 @@ class ClusterModel:
         num_particles, sub_sample = int(num_particles), int(sub_sample)
         if sub_sample < 1 or num_particles % sub_sample != 0:
             raise ValueError("num_particles must be a multiple of sub_sample")
-        if sub_sample != 1:
-            raise NotImplementedError("sub_sample > 1 is only supported for dm/star particles")
         if rng not in ("device", "numpy"):
             raise ValueError("rng must be 'device' or 'numpy'")
         tracer = ptype == "tracer"
@@ -272,12 +270,16 @@ class ClusterModel:
         code = _out_code(dtype)
         keep = []
         a = N.SampleArgs()
+        n_sub = num_particles // sub_sample
+        if sub_sample > 1:
+            a.radius_period = n_sub            # np.tile(radius_sub, sub_sample) (model.py:887-890)
         if rng == "numpy":
-            u_r = prng.uniform(size=num_particles)   # model.py:879-885 -> utils.py:161
+            u_r = prng.uniform(size=n_sub)           # model.py:879-885 -> utils.py:161
             u_ct = prng.uniform(size=num_particles)  # model.py:892
             u_ph = prng.uniform(size=num_particles)  # model.py:893
-            for name, arr in (("d_u_r", u_r), ("d_u_ct", u_ct), ("d_u_ph", u_ph)):
-                t = N.dev_f64(arr[lo:hi], dev)
+            for name, arr in (("d_u_r", u_r if sub_sample > 1 else u_r[lo:hi]), ("d_u_ct", u_ct[lo:hi]),
+                              ("d_u_ph", u_ph[lo:hi])):
+                t = N.dev_f64(arr, dev)
                 keep.append(t)
                 setattr(a.hu, name, t.data_ptr())
             seed = PRIVATE_TRIAL_SEED

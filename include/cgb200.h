@@ -200,6 +200,11 @@ typedef struct cgb_sample_args {
     int32_t *d_trials;       /* nullable */
     double *d_moments;       /* nullable, CGB_NMOMENTS doubles, ACCUMULATED (caller zeroes) */
     cgb_host_uniforms hu;
+    /* cgb_sample_gas only: sub_sample support (model.py:887-890, 911-930).  > 0: the radius
+       (and everything derived from it) of particle id is that of id % radius_period, i.e.
+       np.tile(radius_sub, sub_sample); directions stay per particle.  d_u_r is then the
+       FULL radius_period-long array, indexed by id % radius_period. */
+    int64_t radius_period;
 } cgb_sample_args;
 
 /* P+R+E+V fused: replaces VirialEquilibrium.generate_particles (virial.py:108-236)

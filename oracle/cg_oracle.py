@@ -413,7 +413,7 @@ def generate_gas_particles(model, num_particles, r_max=None, sub_sample=1,
     num_particles_sub = num_particles // sub_sample
     radius_sub, mtot = generate_particle_radii(
         model["radius"], model["gas_mass"], num_particles_sub, r_max=r_max, prng=prng,
-        u=None if uniforms is None else uniforms["u_r"],
+        u=None if uniforms is None else np.asarray(uniforms["u_r"])[:num_particles_sub],
     )
     radius = np.tile(radius_sub, sub_sample)[:num_particles] if sub_sample > 1 else radius_sub
     if uniforms is None:

@@ -377,6 +377,30 @@ def test_gas_particles_match_oracle(oracle):
     assert p.num_particles["gas"] == n
 
 
+def test_gas_and_tracer_sub_sample_and_tracers(oracle):
+    n, s = 40_000, 4
+    om, pm = oracle_model("vikhlinin"), product_model("vikhlinin")
+    fo = oracle.generate_gas_particles(om, n, prng=8, sub_sample=s, compute_potential=True)
+    p = pm.generate_gas_particles(n, prng=8, rng="numpy", sub_sample=s, compute_potential=True)
+    pos = _np(p["gas", "particle_position"])
+    _vec_close(pos, fo["gas", "particle_position"], RTOL64, np.linalg.norm(fo["gas", "particle_position"], axis=1))
+    for f in ("thermal_energy", "density", "particle_mass", "particle_potential"):
+        np.testing.assert_allclose(_np(p["gas", f]), fo["gas", f], rtol=1e-9, err_msg=f)
+    r = np.linalg.norm(pos, axis=1)
+    np.testing.assert_allclose(r[: n // s], r[n // s: 2 * n // s], rtol=1e-12)     # tiled radii
+    with pytest.raises(ValueError):
+        pm.generate_gas_particles(10, sub_sample=3)
+    # tracers: gas-mass CDF, zero mass and velocity (model.py:766-836)
+    t = pm.generate_tracer_particles(5000, prng=3)
+    assert t.num_particles["tracer"] == 5000 and not t["tracer", "particle_mass"].any()
+    assert not t["tracer", "particle_velocity"].any() and torch.isfinite(t["tracer", "particle_position"]).all()
+    # sharded sub-sampled gas equals the single-call result
+    full = pm.generate_gas_particles(n, prng=9, sub_sample=s)
+    parts = [pm.generate_gas_particles(n, prng=9, sub_sample=s, shard=(k, 2)) for k in range(2)]
+    for f in ("particle_position", "density"):
+        assert torch.equal(torch.cat([q["gas", f] for q in parts]), full["gas", f])
+
+
 # --------------------------------------------------------------------------- #
 # reference test-suite invariants (tests/test_particles.py:95-186)
 # --------------------------------------------------------------------------- #

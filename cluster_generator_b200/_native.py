@@ -96,6 +96,8 @@ SYMBOLS = [
     ("cgb_sample_gas", c_int, [POINTER(SampleArgs), c_void_p, c_void_p, c_void_p]),
     ("cgb_ppform_workspace_bytes", c_size_t, [c_int]),
     ("cgb_ppform_prepare", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    ("cgb_map_field", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     ("cgb_resample_gas", c_int, [POINTER(HaloTables), c_int, c_void_p, c_int64, c_int64, c_int, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
 ]

@@ -142,3 +142,90 @@ extern "C" int cgb_resample_gas(const cgb_halo_tables* halos, int num_halos, con
     CGB_CUDA_CHECK(cudaGetLastError());
     return CGB_OK;
 }
+
+// ---------------------------------------------------------------------------
+// 3-D field -> particles, tri-linear  -- replaces ClusterField.map_field_to_particles
+// (fields.py:308-338), i.e. scipy.interpolate.RegularGridInterpolator(method="linear",
+// bounds_error=False, fill_value=0.0) evaluated at the particle positions, for the three
+// vector components at once.  Gather-bound (8 corner loads per component).
+// ---------------------------------------------------------------------------
+struct MapFieldParams {
+    const double *gx, *gy, *gz;
+    int nx, ny, nz;
+    const double* comp[3];
+    int ncomp;
+    const void* pos; long long ld; long long n;
+    void* out;  // (ncomp, ld) planes
+};
+
+// RegularGridInterpolator._find_indices: i = searchsorted(grid, x) - 1 clipped to [0, n-2],
+// norm distance (x - grid[i]) / (grid[i+1] - grid[i]); out of bounds if x outside [g0, g_last]
+__device__ __forceinline__ bool grid_locate(const double* __restrict__ g, int n, double x, int& i, double& t)
+{
+    int lo = 0, hi = n;  // first index with g[idx] >= x  (searchsorted side='left')
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(g + mid) < x) lo = mid + 1; else hi = mid;
+    }
+    i = min(max(lo - 1, 0), n - 2);
+    const double g0 = __ldg(g + i), g1 = __ldg(g + i + 1);
+    t = __ddiv_rn(__dsub_rn(x, g0), __dsub_rn(g1, g0));
+    return !(x < __ldg(g) || x > __ldg(g + n - 1));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) cgb_map_field_kernel(const __grid_constant__ MapFieldParams p)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const T* pos = (const T*)p.pos;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
+        int ix, iy, iz;
+        double tx, ty, tz;
+        bool in = grid_locate(p.gx, p.nx, (double)pos[i], ix, tx);
+        in = grid_locate(p.gy, p.ny, (double)pos[p.ld + i], iy, ty) && in;
+        in = grid_locate(p.gz, p.nz, (double)pos[2 * p.ld + i], iz, tz) && in;
+        for (int c = 0; c < p.ncomp; ++c) {
+            double v = 0.0;
+            if (in) {
+                const double* f = p.comp[c];
+                // corners in itertools.product order, weight = ((1*wx)*wy)*wz, sequential sum
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int b = 0; b < 2; ++b)
+#pragma unroll
+                        for (int d = 0; d < 2; ++d) {
+                            const double wx = a ? tx : __dsub_rn(1.0, tx);
+                            const double wy = b ? ty : __dsub_rn(1.0, ty);
+                            const double wz = d ? tz : __dsub_rn(1.0, tz);
+                            const double w = __dmul_rn(__dmul_rn(wx, wy), wz);
+                            const size_t idx = ((size_t)(ix + a) * p.ny + (size_t)(iy + b)) * p.nz + (size_t)(iz + d);
+                            v = __dadd_rn(v, __dmul_rn(w, __ldg(f + idx)));
+                        }
+            }
+            ((T*)p.out)[(long long)c * p.ld + i] = (T)v;
+        }
+    }
+}
+
+extern "C" int cgb_map_field(const double* d_gx, const double* d_gy, const double* d_gz, int nx, int ny,
+                             int nz, const double* d_fx, const double* d_fy, const double* d_fz,
+                             const void* d_pos, int64_t ld, int64_t n, int dtype, void* d_out, void* stream)
+{
+    CGB_REQUIRE(nx >= 2 && ny >= 2 && nz >= 2 && d_gx && d_gy && d_gz, "cgb_map_field: grid needs >= 2 points per axis");
+    CGB_REQUIRE(d_fx != nullptr, "cgb_map_field: null field");
+    CGB_REQUIRE(dtype == CGB_DTYPE_F64 || dtype == CGB_DTYPE_F32, "cgb_map_field: bad dtype %d", dtype);
+    CGB_REQUIRE(n >= 0 && ld >= n, "cgb_map_field: bad sizes");
+    if (n == 0) return CGB_OK;
+    CGB_REQUIRE(d_pos && d_out, "cgb_map_field: null pointer");
+    MapFieldParams p;
+    p.gx = d_gx; p.gy = d_gy; p.gz = d_gz; p.nx = nx; p.ny = ny; p.nz = nz;
+    p.comp[0] = d_fx; p.comp[1] = d_fy; p.comp[2] = d_fz;
+    p.ncomp = d_fz ? 3 : (d_fy ? 2 : 1);
+    p.pos = d_pos; p.ld = ld; p.n = n; p.out = d_out;
+    const unsigned blocks = (unsigned)min((long long)((n + 255) / 256), 148LL * 16);
+    if (dtype == CGB_DTYPE_F64) cgb_map_field_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    else cgb_map_field_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    CGB_CUDA_CHECK(cudaGetLastError());
+    return CGB_OK;
+}

@@ -275,6 +275,16 @@ int cgb_resample_gas(const cgb_halo_tables *halos, int num_halos, const void *d_
                      int64_t n, int dtype, void *d_density, void *d_thermal, void *d_vel,
                      void *d_mass, int use_radii, void *stream);
 
+/* 3-D field -> particles ("next" row 4): tri-linear interpolation of up to three gridded
+ * components at the particle positions, zero outside the grid.
+ *   replaces ClusterField.map_field_to_particles (fields.py:308-338), i.e.
+ *   RegularGridInterpolator((x, y, z), F, bounds_error=False, fill_value=0.0)(positions).
+ * d_gx/gy/gz: grid coordinates [nx], [ny], [nz] (ascending); d_fx/fy/fz: C-ordered
+ * (nx, ny, nz) components (d_fy, d_fz nullable); d_pos, d_out: (3, ld) / (ncomp, ld) planes. */
+int cgb_map_field(const double *d_gx, const double *d_gy, const double *d_gz, int nx, int ny, int nz,
+                  const double *d_fx, const double *d_fy, const double *d_fz, const void *d_pos,
+                  int64_t ld, int64_t n, int dtype, void *d_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -724,3 +724,32 @@ def test_full_size_properties_config3_headline():
     # stars are more concentrated than the dark matter
     assert float(torch.linalg.norm(p["star", "particle_position"], dim=1).median()) < \
         0.2 * float(torch.linalg.norm(p["dm", "particle_position"], dim=1).median())
+
+
+# --------------------------------------------------------------------------- #
+# "next" row 4: 3-D field -> particles (fields.py:308-338)
+# --------------------------------------------------------------------------- #
+def test_map_field_to_particles_matches_regular_grid_interpolator():
+    from scipy.interpolate import RegularGridInterpolator
+
+    import cluster_generator_b200 as cg
+
+    rng = np.random.RandomState(4)
+    x = np.linspace(-3000.0, 3000.0, 33)
+    y = np.linspace(-2500.0, 2500.0, 29)
+    z = np.sort(rng.uniform(-2000.0, 2000.0, 31))          # non-uniform axis too
+    comps = [rng.normal(size=(33, 29, 31)) for _ in range(3)]
+    pm = product_model("vikhlinin")
+    p = pm.generate_gas_particles(50_000, prng=2)
+    fld = cg.GridField("magnetic_field", x, y, z, comps, units="gauss")
+    fld.map_field_to_particles(p, ptype="gas")
+    pos = _np(p["gas", "particle_position"])
+    got = _np(p["gas", "magnetic_field"])
+    assert got.shape == (50_000, 3) and p.field_units["gas", "magnetic_field"] == "gauss"
+    for i in range(3):
+        ref = RegularGridInterpolator((x, y, z), comps[i], bounds_error=False, fill_value=0.0)(pos)
+        np.testing.assert_allclose(got[:, i], ref, rtol=1e-12, atol=1e-14)
+    outside = (np.abs(pos[:, 0]) > 3000.0) | (np.abs(pos[:, 1]) > 2500.0) | (pos[:, 2] < z[0]) | (pos[:, 2] > z[-1])
+    assert outside.any() and not got[outside].any() and np.abs(got[~outside]).max() > 0
+    with pytest.raises(ValueError):
+        cg.GridField("b", x[::-1], y, z, comps)

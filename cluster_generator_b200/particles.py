@@ -142,6 +142,54 @@ class ClusterParticles:
         self._update_num_particles()
         self._update_field_names()
 
+    # -- persistence ------------------------------------------------------------
+    # The reference writes HDF5 (group per ptype, dataset per field, "units" attribute,
+    # particles.py:337-363).  There is no HDF5 library in this environment, so the same
+    # layout is stored in a NumPy .npz archive: key "<ptype>/<field>", plus "<ptype>/<field>.units".
+    def write_particles(self, output_filename, overwrite=False):
+        """Write the particles to ``output_filename`` (.npz; see the note above)."""
+        import os
+
+        import numpy as np
+
+        output_filename = str(output_filename)
+        if output_filename.endswith((".h5", ".hdf5")):
+            raise NotImplementedError("HDF5 output needs an HDF5 library, which is not available here; "
+                                      "use a .npz file name")
+        if not output_filename.endswith(".npz"):
+            output_filename += ".npz"
+        if os.path.exists(output_filename) and not overwrite:
+            raise IOError(f"Cannot create {output_filename}. It exists and overwrite=False.")
+        data = {}
+        for (ptype, name), t in self.fields.items():
+            data[f"{ptype}/{name}"] = t.detach().cpu().numpy()
+            data[f"{ptype}/{name}.units"] = np.array(self.field_units.get((ptype, name), ""))
+        np.savez(output_filename, **data)
+        return output_filename
+
+    @classmethod
+    def from_file(cls, filename, ptypes=None, device=None):
+        """Read particles written by :meth:`write_particles` (particles.py:235-274)."""
+        import numpy as np
+
+        device = device or ("cuda" if torch.cuda.is_available() else "cpu")
+        z = np.load(str(filename))
+        keys = [k for k in z.files if not k.endswith(".units")]
+        all_ptypes = list(dict.fromkeys(k.split("/")[0] for k in keys))
+        ptypes = all_ptypes if ptypes is None else ensure_list(ptypes)
+        fields = OrderedDict()
+        units = {}
+        for k in keys:
+            ptype, name = k.split("/", 1)
+            if ptype not in ptypes:
+                continue
+            a = torch.from_numpy(z[k]).to(device)
+            fields[ptype, name] = a.T.contiguous().T if a.dim() == 2 else a   # plane-major storage
+            units[ptype, name] = str(z[k + ".units"]) if k + ".units" in z.files else ""
+        out = cls(ptypes, fields)
+        out.field_units.update(units)
+        return out
+
     def to_numpy(self):
         """Host copy: dict (ptype, field) -> ndarray."""
         return {k: v.detach().cpu().numpy() for k, v in self.fields.items()}

@@ -453,7 +453,7 @@ struct PairResult {
 
 // Resolve the undecided trials of a pair on the exact fp64 path.  sa/sb are the screen
 // results; penv == nullptr: the envelope is recomputed from psi (fused mode).
-__device__ __noinline__ PairResult resolve_pair(const Tables& T, const Philox4& w, int sa, int sb,
+__device__ __noinline__ PairResult resolve_pair(const Tables& T, Philox4 w, int sa, int sb,
                                                 double psi, double vesc, const double* penv)
 {
     PairResult r;
@@ -554,10 +554,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
     // (scalars selected by ternaries: dynamically indexed arrays would go to local memory)
     // (read / written only through fully unrolled compare-selects so they stay in registers)
     long long b_loc0[NBUF];
-    int b_cnt[NBUF], b_next[NBUF], b_fin[NBUF];
+    int b_cnt[NBUF];
     bool b_live[NBUF];
 #pragma unroll
-    for (int k = 0; k < NBUF; ++k) { b_loc0[k] = 0; b_cnt[k] = 0; b_next[k] = 0; b_fin[k] = 0; b_live[k] = false; }
+    for (int k = 0; k < NBUF; ++k) { b_loc0[k] = 0; b_cnt[k] = 0; b_live[k] = false; }
 #define BGET(name, b) ([&]() { auto _v = name[0]; _Pragma("unroll") for (int _k = 1; _k < NBUF; ++_k) if ((b) == _k) _v = name[_k]; return _v; }())
 #define BSET(name, b, v) do { _Pragma("unroll") for (int _k = 0; _k < NBUF; ++_k) if ((b) == _k) name[_k] = (v); } while (0)
     bool more_tiles = true;
@@ -608,7 +608,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
         nonpos = __reduce_add_sync(FULL, nonpos);
         if (lane == 0 && nonpos) s_mom[11] += (double)nonpos;
         __syncwarp();
-        BSET(b_loc0, b, loc0); BSET(b_cnt, b, cnt); BSET(b_next, b, 0); BSET(b_fin, b, 0); BSET(b_live, b, true);
+        BSET(b_loc0, b, loc0); BSET(b_cnt, b, cnt); BSET(b_live, b, true);
         return true;
     };
 
@@ -788,7 +788,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
             }
         }
         ++m_coop;
-        BSET(b_fin, s / TILE, BGET(b_fin, s / TILE) + 1);
         if (lane == src) slot = -1;
         __syncwarp();
     };
@@ -823,12 +822,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
         }
     } else {
         // One call site each for acquire() and epilogue() (they are large and inlined): the
-        // loop is a small state machine.  `pending` = buffers whose tile is complete and
-        // must be written out; it starts the ring with cur = NBUF-1 empty so that the first
-        // refill acquires buffer 0.
+        // loop is a small state machine.  `pending` = buffers whose tile is complete and must
+        // be written out.  The hot path keeps the CURRENT buffer's claim state in plain
+        // registers (cur_cnt / cur_next / cur_id0) and only tracks how many particles of the
+        // OTHER (older) buffer are still unfinished (oth_left), so an iteration costs two
+        // ballots beyond the trial itself.
+        static_assert(NBUF == 2, "the lean phase-1 loop assumes two tile buffers per warp");
         unsigned pending = 0;
         bool exiting = false;
-        cur = NBUF - 1;
+        cur = 1;
+        int cur_cnt = 0, cur_next = 0, oth_left = 0;
+        bool oth_live = false;
+        unsigned cur_id0_lo = 0, cur_id0_hi = 0;
         for (;;) {
             while (pending) {
                 const int k = __ffs(pending) - 1;
@@ -836,56 +841,55 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
                 epilogue(k);
             }
             if (exiting) break;
-            // ---- refill idle lanes from the current buffer, rolling to the next tile ----
-            unsigned need = __ballot_sync(FULL, slot < 0);
-            bool restart = false;
-            while (need) {
-                const int avail = BGET(b_cnt, cur) - BGET(b_next, cur);
-                if (avail == 0) {
-                    if (!more_tiles) break;
-                    const int nxt = (cur + 1) % NBUF;  // the oldest buffer of the ring
-                    if (BGET(b_live, nxt)) {
-                        // recycle: its stragglers are finished by the whole warp, then it is
-                        // written out at the top of the loop
-                        finish_lanes(__ballot_sync(FULL, slot >= 0 && slot / TILE == nxt));
-                        pending |= 1u << nxt;
-                        restart = true;
-                        break;
+            // ---- refill idle lanes from the current buffer ----
+            const unsigned need = __ballot_sync(FULL, slot < 0);
+            if (need) {
+                if (cur_next < cur_cnt) {
+                    const int i = cur_next + __popc(need & lt_mask);
+                    cur_next += __popc(need);
+                    if (slot < 0 && i < cur_cnt) {
+                        slot = cur * TILE + i;
+                        ps = (float)s_psi[slot];
+                        vs = (float)(s_ves[slot] * 0x1.0p-32);
+                        es = s_es[slot];
+                        pair = 0;
+                        id_lo = cur_id0_lo + (unsigned)i;
+                        id_hi = cur_id0_hi + (id_lo < cur_id0_lo ? 1u : 0u);
                     }
-                    if (!acquire(nxt)) break;
+                } else {
+                    // current buffer exhausted (rare path): roll to the next tile or drain
+                    const unsigned act = __ballot_sync(FULL, slot >= 0);
+                    if (!more_tiles) {
+                        if (act) finish_lanes(act);  // nothing left to claim anywhere: final drain
+                        if (b_live[0]) pending |= 1u;
+                        if (b_live[1]) pending |= 2u;
+                        exiting = true;
+                        continue;
+                    }
+                    const int nxt = cur ^ 1;
+                    if (oth_live) {
+                        // recycle: the older tile's stragglers are finished by the whole warp,
+                        // then it is written out at the top of the loop
+                        finish_lanes(__ballot_sync(FULL, slot >= 0 && (slot >= TILE) == (nxt == 1)));
+                        oth_live = false;
+                        pending |= 1u << nxt;
+                        continue;
+                    }
+                    if (!acquire(nxt)) continue;  // more_tiles is now false: drains next round
+                    // the buffer we were claiming from becomes the older one
+                    oth_left = __popc(__ballot_sync(FULL, slot >= 0));
+                    oth_live = cur_cnt > 0;
+                    if (oth_live && oth_left == 0) { oth_live = false; pending |= 1u << cur; }
                     cur = nxt;
-                    need = __ballot_sync(FULL, slot < 0);
+                    cur_cnt = BGET(b_cnt, cur);
+                    cur_next = 0;
+                    const unsigned long long id0 = (unsigned long long)(id_base + BGET(b_loc0, cur));
+                    cur_id0_lo = (unsigned)id0; cur_id0_hi = (unsigned)(id0 >> 32);
                     continue;
                 }
-                const int want = __popc(need);
-                const int rank = __popc(need & lt_mask);
-                if (((need >> lane) & 1u) && rank < avail) {
-                    const int i = BGET(b_next, cur) + rank;
-                    slot = cur * TILE + i;
-                    ps = (float)s_psi[slot];
-                    vs = (float)(s_ves[slot] * 0x1.0p-32);
-                    es = s_es[slot];
-                    pair = 0;
-                    const unsigned long long id = (unsigned long long)(id_base + BGET(b_loc0, cur) + i);
-                    id_lo = (unsigned)id; id_hi = (unsigned)(id >> 32);
-                }
-                BSET(b_next, cur, BGET(b_next, cur) + min(want, avail));
-                if (want <= avail) break;
-                need = __ballot_sync(FULL, slot < 0);
-            }
-            if (restart) continue;
-            const unsigned act = __ballot_sync(FULL, slot >= 0);
-            if (act == 0 || (!more_tiles && BGET(b_next, cur) == BGET(b_cnt, cur))) {
-                // nothing left to claim anywhere: final drain, then write out what is held
-                if (act) finish_lanes(act);
-#pragma unroll
-                for (int k = 0; k < NBUF; ++k)
-                    if (b_live[k]) pending |= 1u << k;
-                exiting = true;
-                continue;
             }
             // ---- one Philox call = two trials for every active lane ----
-            bool done = false;
+            bool done_oth = false;
             if (slot >= 0) {
                 const Philox4 w = philox_rk(p.rk, id_lo, id_hi, pair, CGB_STREAM_VEL_TRIAL);
                 const PairResult r = eval_pair(T, s_screen, w, ps, vs, es, s_psi + slot, s_ves + slot,
@@ -894,23 +898,25 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
                 if (r.acc) {
                     s_wa[slot] = (r.acc == 1) ? w.x : w.z;
                     s_tri[slot] = (int)(2u * pair + (unsigned)r.acc);
-                    done = true;
+                    done_oth = (slot >= TILE) != (cur == 1);
+                    slot = -1;
                 } else {
                     ++pair;
                 }
             }
+            // particles of the older tile that just finished; the tile goes out when all did
+            const unsigned dn = __ballot_sync(FULL, done_oth);
+            if (dn) {
+                oth_left -= __popc(dn);
+                if (oth_live && oth_left == 0) { oth_live = false; pending |= 1u << (cur ^ 1); }
+            }
             // long runners leave their lane: the warp finishes them 128 trials at a time
-            const unsigned lng = __ballot_sync(FULL, slot >= 0 && !done && pair >= LANE_CAP_PAIRS);
-            if (lng) finish_lanes(lng);
-            if (lng || __any_sync(FULL, done)) {
-                const int myb = done ? slot / TILE : -1;
-                if (done) slot = -1;
-#pragma unroll
-                for (int k = 0; k < NBUF; ++k) {
-                    b_fin[k] += __popc(__ballot_sync(FULL, myb == k));
-                    // a fully finished tile that is no longer being claimed from goes out
-                    if (k != cur && b_live[k] && b_fin[k] == b_cnt[k]) pending |= 1u << k;
-                }
+            const unsigned lng = __ballot_sync(FULL, slot >= 0 && pair >= LANE_CAP_PAIRS);
+            if (lng) {
+                const unsigned in_oth = __ballot_sync(FULL, slot >= 0 && (slot >= TILE) != (cur == 1));
+                finish_lanes(lng);
+                oth_left -= __popc(lng & in_oth);
+                if (oth_live && oth_left == 0) { oth_live = false; pending |= 1u << (cur ^ 1); }
             }
         }
     }

@@ -753,3 +753,21 @@ def test_map_field_to_particles_matches_regular_grid_interpolator():
     assert outside.any() and not got[outside].any() and np.abs(got[~outside]).max() > 0
     with pytest.raises(ValueError):
         cg.GridField("b", x[::-1], y, z, comps)
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 127, 128, 129, 255, 257, 4095, 4097, 65_537])
+def test_tile_boundaries_parity_sweep(oracle, n):
+    """Particle counts around the warp / tile / CTA boundaries of the sampler (32 lanes,
+    128-particle tiles, 16 warps): every particle must still equal the oracle's."""
+    seed = 1000 + n
+    ov, fo = _oracle_particles(oracle, "nfw_bcg", "dark_matter", n, seed)
+    pv, p = _device_particles("nfw_bcg", "dark_matter", n, seed)
+    _vec_close(_np(p["dm", "particle_position"]), fo["dm", "particle_position"], RTOL64, ov.last["radius"])
+    _vec_close(_np(p["dm", "particle_velocity"]), fo["dm", "particle_velocity"], RTOL64, ov.last["speed"])
+    d = p.diagnostics["dm"].as_dict()
+    assert d["particles"] == n and d["sum_trials"] == ov.last_trials.sum() and d["failures"] == 0
+    # a shard that starts in the middle of a tile reproduces its slice
+    if n > 40:
+        _, q = _device_particles("nfw_bcg", "dark_matter", n, seed, shard=(1, 3))
+        lo, hi = n // 3, (2 * n) // 3
+        assert torch.equal(q["dm", "particle_velocity"], p["dm", "particle_velocity"][lo:hi])

@@ -160,6 +160,19 @@ class ClusterModel:
         return cls._from_scratch(fields, stellar_density=stellar_density, integrator=integrator)
 
     @classmethod
+    def from_dens_and_entr(cls, rmin, rmax, density, entropy, stellar_density=None, num_points=1000,
+                           integrator="host"):
+        """Hydrostatic model from gas density and entropy profiles (model.py:525-563):
+        kT = S n_e^(2/3) with n_e = rho / (mue mp) in cm^-3 (entropy in keV cm^2)."""
+        from .radial_profiles import RadialProfile
+        from .utils import kpc_to_cm
+
+        n_e = RadialProfile(lambda r: density(r) / (mue * mp * kpc_to_cm**3))
+        temperature = RadialProfile(lambda r: entropy(r) * n_e(r) ** (2.0 / 3.0))
+        return cls.from_dens_and_temp(rmin, rmax, density, temperature, stellar_density=stellar_density,
+                                      num_points=num_points, integrator=integrator)
+
+    @classmethod
     def from_dens_and_tden(cls, rmin, rmax, density, total_density, stellar_density=None, num_points=1000):
         """Hydrostatic model from gas density and total density (model.py:565-618)."""
         mylog.info("Computing the profiles from density and total density.")
@@ -180,6 +193,12 @@ class ClusterModel:
         fields["pressure"] = P
         fields["temperature"] = fields["pressure"] * mu * mp / fields["density"] / keV
         return cls._from_scratch(fields, stellar_density=stellar_density)
+
+    def set_rmax(self, r_max):
+        """Truncate the model at ``r_max`` (model.py:271-293; the reference passes kwargs its
+        constructor does not accept -- here the truncated model simply rebuilds f(E) lazily)."""
+        mask = self.fields["radius"].d <= r_max
+        return ClusterModel(int(mask.sum()), OrderedDict((k, v.d[mask]) for k, v in self.fields.items()))
 
     # -- dict protocol (model.py:295-305) ------------------------------------
     def __getitem__(self, key):

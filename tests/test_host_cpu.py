@@ -102,6 +102,23 @@ def test_host_tables_equal_the_oracle_tables():
                                       if k != "temperature" else np.asarray(pm[k]))
 
 
+def test_entropy_constructor_and_set_rmax():
+    """model.py:525-563 (from_dens_and_entr) reduces to from_dens_and_temp; set_rmax truncates."""
+    import cluster_generator_b200 as cg
+    from cluster_generator_b200.utils import kpc_to_cm, mp, mue
+
+    dens = cg.vikhlinin_density_profile(4.2e5, 100.0, 1000.0, 1.0, 0.67, 3.0)
+    temp = cg.vikhlinin_temperature_profile(10.0, 0.0, 2.0, 1.0, 1500.0, 6.0, 80.0, 1.0)
+    entr = cg.RadialProfile(lambda r: temp(r) * (dens(r) / (mue * mp * kpc_to_cm**3)) ** (-2.0 / 3.0))
+    a = cg.ClusterModel.from_dens_and_temp(1.0, 5.0e3, dens, temp, num_points=60)
+    b = cg.ClusterModel.from_dens_and_entr(1.0, 5.0e3, dens, entr, num_points=60)
+    np.testing.assert_allclose(np.asarray(b["temperature"]), np.asarray(a["temperature"]), rtol=1e-12)
+    np.testing.assert_allclose(np.asarray(b["gravitational_potential"]), np.asarray(a["gravitational_potential"]), rtol=1e-9)
+    c = a.set_rmax(1000.0)
+    assert c.num_elements == int((np.asarray(a["radius"]) <= 1000.0).sum()) and c["radius"].d.max() <= 1000.0
+    assert c["radius"].units == "kpc"
+
+
 def test_radius_cdf_table_and_shards():
     from cluster_generator_b200.virial import radius_cdf_table, shard_bounds
     from oracle import cg_oracle as O

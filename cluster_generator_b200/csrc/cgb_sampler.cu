@@ -1103,6 +1103,13 @@ __global__ void __launch_bounds__(256) cgb_gas_kernel(const __grid_constant__ Sa
     const unsigned* cdf_lut = (const unsigned*)(p.base + hdr->off_cdf_lut);
     const int2* cdf_iv = (const int2*)(p.base + hdr->off_cdf_iv);
     const int npi = hdr->n_psi - 3, nai = hdr->n_aux_coef - 3;
+    // table pointers hoisted out of the particle loop (the header lives in global memory)
+    const double* const a0_brk = p.base + hdr->off_aux_brk[0];
+    const double* const a0_pp = p.base + hdr->off_aux_pp[0];
+    const double* const a1_brk = p.base + hdr->off_aux_brk[1];
+    const double* const a1_pp = p.base + hdr->off_aux_pp[1];
+    const double* const ps_brk = p.base + hdr->off_psi_brk;
+    const double* const ps_pp = p.base + hdr->off_psi_pp;
     const long long n_local = p.id_end - p.id_begin;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long loc = (long long)blockIdx.x * blockDim.x + threadIdx.x; loc < n_local; loc += stride) {
@@ -1144,18 +1151,18 @@ __global__ void __launch_bounds__(256) cgb_gas_kernel(const __grid_constant__ Sa
             store_out<OutT>(p.vel, 2 * p.ld + loc, 0.0);
         }
         if (p.mass) store_out<OutT>(p.mass, loc, p.particle_mass);
+        // the splines normally share the radius knots: each walk starts at the previous
+        // answer and only verifies it (pp_walk corrects it if the knots differ)
+        int jw = iv;
         if (aux0) {
-            const double* brk = p.base + hdr->off_aux_brk[0];
-            store_out<OutT>(aux0, loc, pp_eval_at(brk, p.base + hdr->off_aux_pp[0], pp_walk(brk, nai, iv, r), r));
+            jw = pp_walk(a0_brk, nai, jw, r);
+            store_out<OutT>(aux0, loc, pp_eval_at(a0_brk, a0_pp, jw, r));
         }
         if (aux1) {
-            const double* brk = p.base + hdr->off_aux_brk[1];
-            store_out<OutT>(aux1, loc, pp_eval_at(brk, p.base + hdr->off_aux_pp[1], pp_walk(brk, nai, iv, r), r));
+            jw = pp_walk(a1_brk, nai, jw, r);
+            store_out<OutT>(aux1, loc, pp_eval_at(a1_brk, a1_pp, jw, r));
         }
-        if (p.pot) {
-            const double* brk = p.base + hdr->off_psi_brk;
-            store_out<OutT>(p.pot, loc, -pp_eval_at(brk, p.base + hdr->off_psi_pp, pp_walk(brk, npi, iv, r), r));
-        }
+        if (p.pot) store_out<OutT>(p.pot, loc, -pp_eval_at(ps_brk, ps_pp, pp_walk(ps_brk, npi, jw, r), r));
         if (p.radius) p.radius[loc] = r;
     }
 }

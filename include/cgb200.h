@@ -71,9 +71,9 @@ int cgb_measure_ffma_tflops(int iters, double *tflops, void *stream);
 /*   s=0, ext=0) as used at virial.py:41,45,65,67,152 and model.py:909,921,939 */
 /* ------------------------------------------------------------------------ */
 /* Fit: knots t = [x0]*4 + x[2:-2] + [x_{n-1}]*4 (n+4 values), n coefficients.
- * d_work: >= cgb_spline_fit_workspace_bytes(n) bytes.  Returns CGB_E_NOTMONO through
- * *d_status (device int, nullable) -- asynchronous, so monotonicity is reported on
- * the device; the Python wrapper checks it on the host before calling. */
+ * d_work: >= cgb_spline_fit_workspace_bytes(n) bytes.  The call is asynchronous and does
+ * not inspect the data: x must be strictly increasing (scipy raises ValueError for that at
+ * virial.py:45); the Python wrapper checks it on the host, where the tables come from. */
 size_t cgb_spline_fit_workspace_bytes(int n);
 int cgb_spline_fit(const double *d_x, const double *d_y, int n, double *d_t, double *d_c,
                    void *d_work, size_t work_bytes, void *stream);

@@ -771,3 +771,20 @@ def test_tile_boundaries_parity_sweep(oracle, n):
         _, q = _device_particles("nfw_bcg", "dark_matter", n, seed, shard=(1, 3))
         lo, hi = n // 3, (2 * n) // 3
         assert torch.equal(q["dm", "particle_velocity"], p["dm", "particle_velocity"][lo:hi])
+
+
+def test_integration_md_cython_seam_stub_runs_as_documented(oracle):
+    """The ctypes stub INTEGRATION.md tells a maintainer to add is executed verbatim."""
+    import re
+
+    from cluster_generator_b200 import _native as N
+
+    md = open(os.path.join(os.path.dirname(__file__), "..", "INTEGRATION.md")).read()
+    code = re.search(r"```python\n(import ctypes, numpy as np, torch.*?)```", md, re.S).group(1)
+    ns = {}
+    exec(code.replace('"libcgb200.so"', repr(N.LIB_PATH)), ns)
+    n = 20_000
+    ov, last, trials_o = _seam_inputs(oracle, "hernquist", "dark_matter", n, seed=0)
+    vel = ns["generate_velocities"](last["psi"], last["vesc"], last["fv2esc"], ov.f.get_knots(),
+                                    ov.f.get_coeffs(), 3, -2)
+    np.testing.assert_allclose(vel, last["speed"], rtol=RTOL64)

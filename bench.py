@@ -259,6 +259,13 @@ def run_cuda(args):
         ev1.record()
         torch.cuda.synchronize()
         fe_ms.append(ev0.elapsed_time(ev1))
+    cv_ms = []
+    for _ in range(3):
+        ev0.record()
+        pm.dm_virial.check_virial()
+        ev1.record()
+        torch.cuda.synchronize()
+        cv_ms.append(ev0.elapsed_time(ev1))
     dm_tabs = pm.dm_virial.sampler_tables()
     gas_tabs = pm._gas_sampler_tables(None, False)
 
@@ -426,7 +433,7 @@ def run_cuda(args):
         "config": {"workload": WORKLOAD, "dm_per_gpu": n, "gas_per_gpu": n, "num_points": pm.num_elements,
                    "rng": "Philox4x32-10 device", "l2": "outputs 1.28 GB/step/GPU exceed the 126 MB L2",
                    "parallelism": f"index-sharded x{world}"},
-        "fE_build_ms": min(fe_ms), "fE_build_cpu_ms": 1e3 * fe_cpu_s,
+        "fE_build_ms": min(fe_ms), "fE_build_cpu_ms": 1e3 * fe_cpu_s, "check_virial_ms": min(cv_ms),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "what": "ClusterModel.generate_dm_particles + generate_gas_particles from host tables, all fields copied to pinned host memory"},
         "gpu_launches": 2 * args.steps,

@@ -24,6 +24,7 @@ CGB_E_NOTMONO = -4
 CGB_DTYPE_F64 = 0
 CGB_DTYPE_F32 = 1
 CGB_NMOMENTS = 16
+CGB_FIT_FITPACK, CGB_FIT_PCR = 0, 1
 MOMENT_NAMES = (
     "particles", "sum_trials", "max_trials", "sum_v2", "sum_psi", "sum_x", "sum_y", "sum_z",
     "sum_vx", "sum_vy", "sum_vz", "nonpositive_envelopes", "cooperative_finishes", "failures",
@@ -73,11 +74,11 @@ SYMBOLS = [
     ("cgb_measure_dfma_tflops", c_int, [c_int, POINTER(c_double), c_void_p]),
     ("cgb_measure_ffma_tflops", c_int, [c_int, POINTER(c_double), c_void_p]),
     ("cgb_spline_fit_workspace_bytes", c_size_t, [c_int]),
-    ("cgb_spline_fit", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    ("cgb_spline_fit", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     ("cgb_spline_eval", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     ("cgb_eddington_workspace_bytes", c_size_t, [c_int]),
     ("cgb_eddington_df", c_int, [c_void_p, c_void_p, c_int, c_double, c_double, c_void_p, c_void_p,
-                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     ("cgb_check_virial", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p]),
     ("cgb_integrate_spline", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_double,

@@ -682,9 +682,11 @@ extern "C" size_t cgb_eddington_workspace_bytes(int n)
 extern "C" int cgb_eddington_df(const double* d_ee, const double* d_pden, int n, double epsabs,
                                 double epsrel, double* d_g, double* d_ff, double* d_f_t,
                                 double* d_f_c, int* d_last, int* d_ier, void* d_work,
-                                size_t work_bytes, void* stream)
+                                size_t work_bytes, int fit_method, void* stream)
 {
     CGB_REQUIRE(n >= 8, "cgb_eddington_df: need at least 8 radial points, got %d", n);
+    CGB_REQUIRE(fit_method == CGB_FIT_FITPACK || fit_method == CGB_FIT_PCR,
+                "cgb_eddington_df: unknown fit method %d", fit_method);
     CGB_REQUIRE(d_ee && d_pden && d_g && d_ff && d_f_t && d_f_c && d_work,
                 "cgb_eddington_df: null pointer");
     if (work_bytes < cgb_eddington_workspace_bytes(n)) {
@@ -703,7 +705,7 @@ extern "C" int cgb_eddington_df(const double* d_ee, const double* d_pden, int n,
     void* fit_scratch = w;
     int rc;
     // density_spline = IUS(ee, pden)                                  (virial.py:45)
-    if ((rc = cgb_launch_spline_fit(d_ee, d_pden, n, t_rho, c_rho, fit_scratch, s))) return rc;
+    if ((rc = cgb_launch_spline_fit(d_ee, d_pden, n, t_rho, c_rho, fit_scratch, s, fit_method))) return rc;
     if ((rc = cgb_launch_splder_coeffs(t_rho, c_rho, n, wrk, s))) return rc;
     const size_t smem = edd_smem_bytes(n);
     CGB_REQUIRE(smem <= 227 * 1024, "cgb_eddington_df: n = %d needs %zu B of shared memory", n, smem);
@@ -713,13 +715,13 @@ extern "C" int cgb_eddington_df(const double* d_ee, const double* d_pden, int n,
         d_ee, n, t_rho, wrk, epsabs, epsrel, d_g, d_last, d_ier);
     CGB_CUDA_CHECK(cudaGetLastError());
     // g_spline = IUS(ee, g); ff = g_spline(ee, 1) / (sqrt(8) pi^2)    (virial.py:65-66)
-    if ((rc = cgb_launch_spline_fit(d_ee, d_g, n, t_g, c_g, fit_scratch, s))) return rc;
+    if ((rc = cgb_launch_spline_fit(d_ee, d_g, n, t_g, c_g, fit_scratch, s, fit_method))) return rc;
     if ((rc = cgb_launch_splder_coeffs(t_g, c_g, n, wrk_g, s))) return rc;
     const double den = sqrt(8.0) * (M_PI * M_PI);
     cgb_ff_kernel<<<(n + 255) / 256, 256, 0, s>>>(t_g, wrk_g, n, d_ee, den, d_ff);
     CGB_CUDA_CHECK(cudaGetLastError());
     // self.f = IUS(ee, ff)                                            (virial.py:67)
-    if ((rc = cgb_launch_spline_fit(d_ee, d_ff, n, d_f_t, d_f_c, fit_scratch, s))) return rc;
+    if ((rc = cgb_launch_spline_fit(d_ee, d_ff, n, d_f_t, d_f_c, fit_scratch, s, fit_method))) return rc;
     return CGB_OK;
 }
 

@@ -4,7 +4,7 @@
 
 // d_work: n*6 doubles (band[n][5], rhs[n])
 int cgb_launch_spline_fit(const double* d_x, const double* d_y, int n, double* d_t, double* d_c,
-                          void* d_work, cudaStream_t s);
+                          void* d_work, cudaStream_t s, int method);
 // d_wrk: n-1 doubles
 int cgb_launch_splder_coeffs(const double* d_t, const double* d_c, int n, double* d_wrk, cudaStream_t s);
 // d_brk: n-2 doubles, d_pp: (n-3)*4 doubles

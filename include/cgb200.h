@@ -73,10 +73,16 @@ int cgb_measure_ffma_tflops(int iters, double *tflops, void *stream);
 /* Fit: knots t = [x0]*4 + x[2:-2] + [x_{n-1}]*4 (n+4 values), n coefficients.
  * d_work: >= cgb_spline_fit_workspace_bytes(n) bytes.  The call is asynchronous and does
  * not inspect the data: x must be strictly increasing (scipy raises ValueError for that at
- * virial.py:45); the Python wrapper checks it on the host, where the tables come from. */
+ * virial.py:45); the Python wrapper checks it on the host, where the tables come from.
+ * method: CGB_FIT_FITPACK = fpcurf's own Givens-rotation solve, coefficients bit-equal to
+ * scipy's (serial recurrence, ~0.3 ms for n = 1000; used by the f(E) build, whose quadrature
+ * decisions and spline derivative amplify coefficient noise); CGB_FIT_PCR = parallel cyclic
+ * reduction of the same collocation system, ~20 us, coefficients within 1e-13 of FITPACK's. */
+#define CGB_FIT_FITPACK 0
+#define CGB_FIT_PCR 1
 size_t cgb_spline_fit_workspace_bytes(int n);
 int cgb_spline_fit(const double *d_x, const double *d_y, int n, double *d_t, double *d_c,
-                   void *d_work, size_t work_bytes, void *stream);
+                   void *d_work, size_t work_bytes, int method, void *stream);
 /* Evaluate the spline (nu = 0) or its first derivative (nu = 1) at m points
  * (FITPACK splev/splder arithmetic, extrapolating outside the knots). */
 int cgb_spline_eval(const double *d_t, const double *d_c, int n, const double *d_x, double *d_y,
@@ -91,11 +97,14 @@ int cgb_spline_eval(const double *d_t, const double *d_c, int n, const double *d
  *      (virial.py:65-66), and the spline of ff: d_f_t[n+4], d_f_c[n] (virial.py:67).
  *      d_last[n], d_ier[n] (nullable): QAGS sub-interval count / error flag per bin.
  * The quadrature is a decision-for-decision restatement of QUADPACK dqagse
- * (21-point Gauss-Kronrod, bisection, epsilon extrapolation, limit = 50). */
+ * (21-point Gauss-Kronrod, bisection, epsilon extrapolation, limit = 50).
+ * fit_method: CGB_FIT_FITPACK makes g, ff and the f spline bit-equal to scipy's (the three
+ * spline fits use fpcurf's own solve, ~1.2 ms each); CGB_FIT_PCR is ~10x faster overall and
+ * within 1e-11 of it. */
 size_t cgb_eddington_workspace_bytes(int n);
 int cgb_eddington_df(const double *d_ee, const double *d_pden, int n, double epsabs, double epsrel,
                      double *d_g, double *d_ff, double *d_f_t, double *d_f_c, int *d_last,
-                     int *d_ier, void *d_work, size_t work_bytes, void *stream);
+                     int *d_ier, void *d_work, size_t work_bytes, int fit_method, void *stream);
 
 /* ------------------------------------------------------------------------ */
 /* C: virial self-check                                                      */

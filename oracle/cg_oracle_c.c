@@ -770,3 +770,62 @@ int cgo_generate_velocities_array(const double *psi, const double *vesc, const d
     free(t);
     return 0;
 }
+
+/* ------------------------------------------------------------------------- */
+/* FITPACK fpcurf for the interpolating case (s = 0, k = 3, unit weights):   */
+/* observation rows rotated into an upper-triangular band matrix by Givens   */
+/* transformations (fpgivs / fprota), then back substitution (fpback).       */
+/* Restated from P. Dierckx's published algorithm; pinned bit-for-bit        */
+/* against scipy's InterpolatedUnivariateSpline in tests/test_oracle_cpu.py. */
+/* ------------------------------------------------------------------------- */
+int cgo_spline_fit_fitpack(const double *x, const double *y, int64_t m, double *t, double *c)
+{
+    if (m < 4) return -1;
+    const int k = 3, k1 = 4;
+    int64_t n = m + 4, nk1 = n - k1;
+    for (int i = 0; i < 4; ++i) { t[i] = x[0]; t[n - 1 - i] = x[m - 1]; }
+    for (int64_t i = 2; i <= m - 3; ++i) t[i + 2] = x[i];
+    double *a = (double *)calloc((size_t)nk1 * k1, sizeof(double)); /* a[j][0..3] */
+    double *z = (double *)calloc((size_t)nk1, sizeof(double));
+    if (!a || !z) return -2;
+    int64_t l = k1; /* 1-based knot interval index as in fpcurf */
+    for (int64_t it = 1; it <= m; ++it) {
+        double xi = x[it - 1], yi = y[it - 1], h[5];
+        /* search for knot interval t(l) <= xi < t(l+1) */
+        while (!(xi < t[l] || l == nk1)) ++l; /* t(l+1) in 1-based == t[l] 0-based */
+        fpbspl(t, k, xi, l - 1, h);          /* 0-based interval index l-1 */
+        int64_t j = l - k1;                  /* 1-based row j+1 .. */
+        for (int i = 1; i <= k1; ++i) {
+            ++j;
+            double piv = h[i - 1];
+            if (piv == 0.0) continue;
+            double *aj = a + (size_t)(j - 1) * k1;
+            /* fpgivs */
+            double ww = aj[0], store = fabs(piv), dd, co, si;
+            if (store >= ww) dd = store * sqrt(1.0 + (ww / piv) * (ww / piv));
+            else dd = ww * sqrt(1.0 + (piv / ww) * (piv / ww));
+            co = ww / dd; si = piv / dd; aj[0] = dd;
+            /* fprota on (yi, z(j)) */
+            { double s1 = yi, s2 = z[j - 1]; z[j - 1] = co * s2 + si * s1; yi = co * s1 - si * s2; }
+            if (i == k1) break;
+            int i2 = 0;
+            for (int i1 = i + 1; i1 <= k1; ++i1) {
+                ++i2;
+                double s1 = h[i1 - 1], s2 = aj[i2];
+                aj[i2] = co * s2 + si * s1;
+                h[i1 - 1] = co * s1 - si * s2;
+            }
+        }
+    }
+    /* fpback */
+    c[nk1 - 1] = z[nk1 - 1] / a[(size_t)(nk1 - 1) * k1];
+    for (int64_t i = nk1 - 1; i >= 1; --i) {
+        double store = z[i - 1];
+        int64_t i1 = (nk1 - i < k1 - 1) ? nk1 - i : k1 - 1;
+        int64_t mm = i;
+        for (int64_t ll = 1; ll <= i1; ++ll) { ++mm; store -= c[mm - 1] * a[(size_t)(i - 1) * k1 + ll]; }
+        c[i - 1] = store / a[(size_t)(i - 1) * k1];
+    }
+    free(a); free(z);
+    return 0;
+}

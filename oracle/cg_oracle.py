@@ -577,6 +577,8 @@ def clib():
         lib.cgo_check_virial_rho.restype = ctypes.c_int
         lib.cgo_spline_fit.argtypes = [dp, dp, ctypes.c_int64, dp, dp]
         lib.cgo_spline_fit.restype = ctypes.c_int
+        lib.cgo_spline_fit_fitpack.argtypes = [dp, dp, ctypes.c_int64, dp, dp]
+        lib.cgo_spline_fit_fitpack.restype = ctypes.c_int
         _CLIB = lib
     return _CLIB
 

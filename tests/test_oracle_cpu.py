@@ -77,6 +77,21 @@ def test_c_spline_fit_reproduces_fitpack(oracle, name):
     np.testing.assert_allclose(c, c_ref[: x.size], rtol=1e-13)
 
 
+@pytest.mark.parametrize("name", ["hernquist", "nfw_bcg", "vikhlinin"])
+def test_c_fpcurf_givens_fit_is_bit_equal_to_fitpack(oracle, name):
+    """fpcurf's own solve (Givens rotations + fpback) restated: coefficients equal scipy's bits."""
+    om = oracle_model(name)
+    for x, y in ((-om["gravitational_potential"][::-1], om["dark_matter_density"][::-1]),
+                 (om["radius"], -om["gravitational_potential"])):
+        x, y = np.ascontiguousarray(x), np.ascontiguousarray(y)
+        t_ref, c_ref, _ = IUS(x, y)._eval_args
+        t, c = np.empty(x.size + 4), np.empty(x.size)
+        assert oracle.clib().cgo_spline_fit_fitpack(oracle._dptr(x), oracle._dptr(y), x.size,
+                                                    oracle._dptr(t), oracle._dptr(c)) == 0
+        np.testing.assert_array_equal(t, t_ref)
+        np.testing.assert_array_equal(c, c_ref[: x.size])
+
+
 # ---- third-party arithmetic: QUADPACK -------------------------------------------------- #
 def _c_quad(oracle, f, a, b, eps, limit=50):
     CB = ctypes.CFUNCTYPE(ctypes.c_double, ctypes.c_double, ctypes.c_void_p)

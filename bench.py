@@ -440,7 +440,8 @@ def run_cuda(args):
         "fE_build_cpu_ms": 1e3 * fe_cpu_s, "check_virial_ms": min(cv_ms),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "what": "ClusterModel.generate_dm_particles + generate_gas_particles from host tables, all fields copied to pinned host memory"},
-        "gpu_launches": 2 * args.steps,
+        # per step: cgb_sample_kernel + cgb_hard_kernel (deferred long-tail pass) + cgb_gas_kernel
+        "gpu_launches": 3 * args.steps,
         "roofline": roofline,
         "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port",
                          "sample": f"{n_cpu} DM + {n_cpu} gas particles, oracle mode A C loop + numpy, {cpu_dt:.1f} s",

@@ -377,14 +377,36 @@ __device__ __forceinline__ void load_tables(const double* base, Tables& T)
     T.f_scale = hdr->f_scale;
 }
 
-// the screen table in shared memory: NB buckets + one sentinel (-inf, +inf) that every
-// out-of-range bucket index is clamped to, so such trials come out "undecided"
-__device__ __forceinline__ void load_screen(const double* base, float2* s_screen)
+// The screen table in shared memory: NB buckets + one sentinel (-inf, +inf) that every
+// out-of-range bucket index is clamped to, so such trials come out "undecided".
+// The 32 KB table is staged with one TMA bulk copy (cp.async.bulk, completion on an
+// mbarrier) issued by thread 0 while the other threads set up their state.
+__device__ __forceinline__ void load_screen(const double* base, float2* s_screen, unsigned long long* mbar)
 {
     const SamplerHeader* hdr = (const SamplerHeader*)base;
     const float2* g = (const float2*)(base + hdr->off_screen);
-    for (int i = threadIdx.x; i < NB; i += blockDim.x) s_screen[i] = g[i];
-    if (threadIdx.x == 0) s_screen[NB] = make_float2(-INFINITY, INFINITY);
+    const unsigned mbar_a = (unsigned)__cvta_generic_to_shared(mbar);
+    const unsigned dst_a = (unsigned)__cvta_generic_to_shared(s_screen);
+    constexpr unsigned BYTES = NB * sizeof(float2);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_a) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_a), "r"(BYTES) : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_a),
+            "l"(g), "r"(BYTES), "r"(mbar_a)
+            : "memory");
+        s_screen[NB] = make_float2(-INFINITY, INFINITY);
+    }
+    __syncthreads();  // the barrier is initialised and armed for everyone
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+            : "=r"(done)
+            : "r"(mbar_a)
+            : "memory");
+    }
 }
 
 // largest j in [0, n_cdf-2] with P[j] <= u       (np.interp's interval, utils.py:165)
@@ -538,10 +560,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
     const unsigned FULL = 0xffffffffu;
     const unsigned lt_mask = (1u << lane) - 1u;
 
+    __shared__ unsigned long long s_mbar;
     Tables T;
     load_tables(p.base, T);
-    load_screen(p.base, s_screen);
     if (lane < CGB_NMOMENTS) s_mom[lane] = 0.0;
+    load_screen(p.base, s_screen, &s_mbar);
     __syncthreads();
 
     unsigned long long m_exact = 0;  // per-lane exact-evaluation counter
@@ -959,9 +982,10 @@ __global__ void __launch_bounds__(512, 1) cgb_hard_kernel(const __grid_constant_
     __shared__ int s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned FULL = 0xffffffffu;
+    __shared__ unsigned long long s_mbar;
     Tables T;
     load_tables(p.base, T);
-    load_screen(p.base, s_screen);
+    load_screen(p.base, s_screen, &s_mbar);
     __syncthreads();
     HardEntry* ent = (HardEntry*)(sh + 1);
     for (unsigned h = 0; h < n_hard; ++h) {

@@ -43,27 +43,6 @@ struct Philox4 {
     uint32_t x, y, z, w;
 };
 
-__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
-                                                 uint32_t c3, uint32_t k0, uint32_t k1)
-{
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(CGB_PHILOX_M0, c0);
-        const uint32_t lo0 = CGB_PHILOX_M0 * c0;
-        const uint32_t hi1 = __umulhi(CGB_PHILOX_M1, c2);
-        const uint32_t lo1 = CGB_PHILOX_M1 * c2;
-        c0 = hi1 ^ c1 ^ k0;
-        c1 = lo1;
-        c2 = hi0 ^ c3 ^ k1;
-        c3 = lo0;
-        k0 += CGB_PHILOX_W0;
-        k1 += CGB_PHILOX_W1;
-    }
-    Philox4 o;
-    o.x = c0; o.y = c1; o.z = c2; o.w = c3;
-    return o;
-}
-
 // 52-bit uniform in [0,1): [1,2) - 1 with mantissa (hi:32 | lo>>12)
 __device__ __forceinline__ double u52(uint32_t hi, uint32_t lo)
 {

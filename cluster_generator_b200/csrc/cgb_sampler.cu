@@ -13,19 +13,22 @@
 //   * every quantity of particle `id` is a pure function of (tables, seed, id): Philox
 //     counter = (id, trial pair), so results do not depend on scheduling or on how
 //     the index range is sharded over GPUs.
-//   * each WARP owns a tile of TILE consecutive ids, claimed from a global atomic
-//     counter.  Phase 0 (uniform): radius, psi, envelope for the whole tile into
-//     shared memory.  Phase 1 (divergent): one particle per lane, lanes refill from
-//     the tile as they accept (ballot + popc), two trials per Philox call.  When the
-//     tile runs dry, or a particle exceeds LANE_CAP trials, the warp finishes that
-//     particle cooperatively (64 trials per step, first accepted trial wins).
+//   * each WARP owns two rolling buffers of TILE consecutive ids, claimed from a
+//     global atomic counter.  Phase 0 (uniform): radius, psi, envelope for a whole
+//     buffer into shared memory.  Phase 1 (divergent): one particle per lane, lanes
+//     refill from the buffers as they accept (ballot + popc), two trials per Philox
+//     call; the next buffer is filled while stragglers of the previous one finish.
+//     A particle that exceeds LANE_CAP_PAIRS trial pairs, or is left over when the
+//     index range runs dry, is finished by the whole warp cooperatively (64 trials
+//     per step, first accepted trial wins); one that exceeds HARD_PAIRS pairs is
+//     deferred to cgb_hard_kernel, which spreads its trials over the whole grid.
 //     Phase 2 (uniform): directions, spherical->Cartesian, coalesced plane stores.
 //   * the accept test f(psi - v^2/2) v^2 >= u2 * fv2esc is first tried on a
 //     conservative fp32 interval screen: a 4096-bucket table of rigorous lower/upper
-//     bounds of f over each energy bucket, resident in shared memory (one 8-byte
-//     load per trial).  Only when the screen cannot decide (~0.3 % of trials) is the
-//     exact fp64 piecewise-polynomial spline evaluated, so accept/reject decisions
-//     are identical to the exact evaluation by construction.
+//     bounds of f over each energy bucket, staged into shared memory by one TMA bulk
+//     copy per CTA (one 8-byte load per trial).  Only when the screen cannot decide
+//     (~4e-4 of trials) is the exact fp64 piecewise-polynomial spline evaluated, so
+//     accept/reject decisions are identical to the exact evaluation by construction.
 #include <math.h>
 #include <float.h>
 #include "cgb_common.cuh"
@@ -1232,15 +1235,6 @@ cgb_assemble_kernel(SampleParams p, const double* __restrict__ r_sub, const doub
         if (p.mass) store_out<OutT>(p.mass, loc, p.particle_mass);
         if (p.pot && psi_sub) store_out<OutT>(p.pot, loc, -psi_sub[js]);
     }
-}
-
-// psi at given radii (for the sub_sample potential): psi = energy_spline(radius_sub)
-__global__ void cgb_psi_at_kernel(const double* __restrict__ base, const double* __restrict__ r,
-                                  double* __restrict__ psi, long long n)
-{
-    const SamplerHeader* hdr = (const SamplerHeader*)base;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) psi[i] = pp_eval(base + hdr->off_psi_brk, base + hdr->off_psi_pp, hdr->n_psi - 3, r[i]);
 }
 
 // ---------------------------------------------------------------------------

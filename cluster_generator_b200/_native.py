@@ -21,6 +21,7 @@ CGB_E_INVALID = -1
 CGB_E_CUDA = -2
 CGB_E_WORKSPACE = -3
 CGB_E_NOTMONO = -4
+CGB_E_IO = -5
 CGB_DTYPE_F64 = 0
 CGB_DTYPE_F32 = 1
 CGB_NMOMENTS = 16
@@ -101,6 +102,23 @@ SYMBOLS = [
                               c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     ("cgb_resample_gas", c_int, [POINTER(HaloTables), c_int, c_void_p, c_int64, c_int64, c_int, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    ("cgb_h5_create", c_int, [c_char_p, c_int, POINTER(c_void_p)]),
+    ("cgb_h5_create_group", c_int, [c_void_p, c_char_p]),
+    ("cgb_h5_write_dataset", c_int, [c_void_p, c_char_p, c_int, c_int, POINTER(c_int64), c_void_p]),
+    ("cgb_h5_write_dataset_device", c_int, [c_void_p, c_char_p, c_int, c_void_p, c_int, c_int64, c_int, c_int64,
+                                            c_double, c_void_p]),
+    ("cgb_h5_set_attr", c_int, [c_void_p, c_char_p, c_char_p, c_int, c_int64, c_void_p]),
+    ("cgb_h5_close", c_int, [c_void_p]),
+    ("cgb_h5_open", c_int, [c_char_p, POINTER(c_void_p)]),
+    ("cgb_h5_num_children", c_int, [c_void_p, c_char_p, POINTER(c_int)]),
+    ("cgb_h5_child_name", c_int, [c_void_p, c_char_p, c_int, c_char_p, c_int, POINTER(c_int)]),
+    ("cgb_h5_dataset_info", c_int, [c_void_p, c_char_p, POINTER(c_int), POINTER(c_int), POINTER(c_int64),
+                                    POINTER(c_int64)]),
+    ("cgb_h5_read_dataset", c_int, [c_void_p, c_char_p, c_void_p, c_size_t]),
+    ("cgb_h5_num_attrs", c_int, [c_void_p, c_char_p, POINTER(c_int)]),
+    ("cgb_h5_attr_name", c_int, [c_void_p, c_char_p, c_int, c_char_p, c_int]),
+    ("cgb_h5_attr_info", c_int, [c_void_p, c_char_p, c_char_p, POINTER(c_int), POINTER(c_int64), POINTER(c_size_t)]),
+    ("cgb_h5_read_attr", c_int, [c_void_p, c_char_p, c_char_p, c_void_p, c_size_t]),
 ]
 
 _LIB = None
@@ -147,6 +165,8 @@ def check(rc: int) -> None:
     msg = lib().cgb_last_error().decode("utf-8", "replace")
     if rc in (CGB_E_INVALID, CGB_E_NOTMONO):
         raise ValueError(msg)
+    if rc == CGB_E_IO:
+        raise IOError(msg)
     raise RuntimeError(f"libcgb200 error {rc}: {msg}")
 
 

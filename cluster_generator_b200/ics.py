@@ -7,9 +7,11 @@ budget over halos by enclosed mass, generate DM / star / gas / tracer particles 
 halo from ONE shared ``prng`` (stream order matters, ics.py:173-192), then offset and
 combine them, re-sampling the gas fields where halos overlap.
 
-Difference from the reference: ``profiles`` are :class:`ClusterModel` objects, not HDF5
-file names -- there is no HDF5 library in this environment, so the file round trip
-(``from_h5_file`` / ``write_particles``) is out of scope and nothing is written to disk.
+``profiles`` are HDF5 model files (``ClusterModel.write_model_to_h5``) as in the reference, or
+:class:`ClusterModel` objects directly.  With an ``output_directory`` the per-halo particles
+are written to ``{output_directory}/{basename}_{i}_particles.h5`` and reused on the next call
+unless ``regenerate_particles`` (ics.py:173-199); without one nothing touches the disk (the
+reference would write to the file-system root).
 """
 from __future__ import annotations
 
@@ -18,7 +20,7 @@ from numbers import Number
 
 import numpy as np
 
-from .particles import combine_three_clusters, combine_two_clusters
+from .particles import ClusterParticles, combine_three_clusters, combine_two_clusters
 from .utils import ensure_list, parse_prng
 
 
@@ -42,11 +44,10 @@ class ClusterICs:
         self.profiles = ensure_list(profiles)
         if len(self.profiles) != self.num_halos:
             raise ValueError("one profile (ClusterModel) per halo is required")
-        if any(isinstance(p, (str, bytes)) for p in self.profiles):
-            raise NotImplementedError(
-                "profile files need HDF5, which is not available here: pass ClusterModel objects")
+        self.particle_files = [None] * self.num_halos
         if particle_files is not None:
-            raise NotImplementedError("particle files need HDF5, which is not available here")
+            self.particle_files = ensure_list(particle_files)[:]
+        self._models = None
         self.center = np.asarray(center, dtype=np.float64).reshape(self.num_halos, 3)
         self.velocity = np.asarray(velocity, dtype=np.float64).reshape(self.num_halos, 3)
         self.mag_file = mag_file
@@ -61,10 +62,20 @@ class ClusterICs:
         self.tot_np = num_particles if num_particles is not None else {"dm": 0, "gas": 0, "star": 0, "tracer": 0}
         self._determine_num_particles()
 
+    @property
+    def models(self):
+        """The halos' :class:`ClusterModel` objects (profile files are read once)."""
+        if self._models is None:
+            from .model import ClusterModel
+
+            self._models = [p if isinstance(p, ClusterModel) else ClusterModel.from_h5_file(p)
+                            for p in self.profiles]
+        return self._models
+
     def _determine_num_particles(self):
         """n_i = rint(N_tot * M_i(<r_max) / sum M) per species (ics.py:100-160)."""
         dm_masses, gas_masses, star_masses, tracer_masses = [], [], [], []
-        for i, p in enumerate(self.profiles):
+        for i, p in enumerate(self.models):
             idxs = p["radius"].d < self.r_max[i]
             dm_masses.append(p["dark_matter_mass"].d[idxs][-1])
             gas_masses.append(p["gas_mass"].d[idxs][-1] if "gas_mass" in p else 0.0)
@@ -90,7 +101,10 @@ class ClusterICs:
         """ics.py:162-200: dm -> star -> gas -> tracer per halo, one shared prng."""
         prng = parse_prng(prng)
         parts = []
-        for i, m in enumerate(self.profiles):
+        for i, m in enumerate(self.models):
+            if not (regenerate_particles or self.particle_files[i] is None):
+                parts.append(ClusterParticles.from_file(self.particle_files[i]))
+                continue
             p = m.generate_dm_particles(self.num_particles["dm"][i], r_max=self.r_max[i], prng=prng, **kw)
             if self.num_particles["star"][i] > 0:
                 p = p + m.generate_star_particles(self.num_particles["star"][i], r_max=self.r_max[i],
@@ -102,11 +116,15 @@ class ClusterICs:
                 p = p + m.generate_tracer_particles(self.num_particles["tracer"][i],
                                                     r_max=self.r_max_tracer[i], prng=prng, **kw)
             parts.append(p)
+            if output_directory is not None:
+                outfile = f"{output_directory}/{self.basename}_{i}_particles.h5"
+                p.write_particles(outfile, overwrite=True)
+                self.particle_files[i] = outfile
         return parts
 
     def setup_particle_ics(self, output_directory=None, regenerate_particles=False, prng=None, **kw):
         """Generate and combine the particles of all halos (ics.py:323-375)."""
-        profiles = self.profiles
+        profiles = self.models
         parts = self._generate_particles(output_directory=output_directory,
                                          regenerate_particles=regenerate_particles, prng=prng, **kw)
         if self.num_halos == 1:

@@ -69,6 +69,68 @@ class ClusterModel:
             self._star_virial = VirialEquilibrium(self, "stellar")
         return self._star_virial
 
+    # -- model files (model.py:149-211, 342-397) -----------------------------
+    _keep_units = ["entropy", "electron_number_density", "magnetic_field_strength"]
+
+    def write_model_to_h5(self, output_filename, in_cgs=False, r_min=None, r_max=None, overwrite=False):
+        """Write the model tables to HDF5 in the reference's layout: scalar dataset
+        ``num_elements``, root attribute ``unit_system``, ``fields/<name>`` datasets with a
+        ``units`` attribute, and ``dm_df`` / ``star_df`` when the distribution functions exist."""
+        import os
+
+        from .h5io import H5Writer
+
+        if in_cgs:
+            raise NotImplementedError("only galactic units (kpc, Msun, Myr) are written; cgs output needs unyt")
+        if os.path.exists(output_filename) and not overwrite:
+            raise IOError(f"Cannot create {output_filename}. It exists and overwrite=False.")
+        r_min = 0.0 if r_min is None else r_min
+        r_max = self.fields["radius"].d[-1] * 2 if r_max is None else r_max
+        mask = np.logical_and(self.fields["radius"].d >= r_min, self.fields["radius"].d <= r_max)
+        with H5Writer(output_filename, overwrite=True) as f:
+            f.write("/num_elements", np.asarray(self.num_elements, dtype=np.int64))
+            f.set_attr("/", "unit_system", "galactic")
+            f.create_group("/fields")
+            for k, v in self.fields.items():
+                f.write(f"/fields/{k}", v.d[mask])
+                f.set_attr(f"/fields/{k}", "units", v.units or "dimensionless")
+            for name, vir in (("dm_df", self._dm_virial), ("star_df", self._star_virial)):
+                if vir is not None:
+                    f.write(f"/{name}", vir.df.d)
+                    f.set_attr(f"/{name}", "units", vir.df.units)
+        return output_filename
+
+    @classmethod
+    def from_h5_file(cls, filename, r_min=None, r_max=None):
+        """Read a model written by :meth:`write_model_to_h5` (or by the reference in galactic
+        units).  A stored ``dm_df`` / ``star_df`` is reused instead of rebuilding f(E)."""
+        from .h5io import H5Reader
+
+        fields = OrderedDict()
+        df = {}
+        with H5Reader(filename) as f:
+            for name in f.keys("/fields"):
+                units = f.attrs(f"/fields/{name}").get("units", _UNITS.get(name, ""))
+                units = "" if units == "dimensionless" else units
+                if name in _UNITS and units != _UNITS[name] and name not in cls._keep_units:
+                    raise ValueError(f"field {name!r} is stored in {units!r}; only galactic units "
+                                     f"({_UNITS[name]!r}) can be read without unyt")
+                fields[name] = unit_array(f.read(f"/fields/{name}").astype(np.float64), units)
+            for name in ("dm_df", "star_df"):
+                if name in f.keys("/"):
+                    df[name] = f.read(f"/{name}").astype(np.float64)
+        r_min = 0.0 if r_min is None else r_min
+        r_max = fields["radius"].d[-1] * 2 if r_max is None else r_max
+        mask = np.logical_and(fields["radius"].d >= r_min, fields["radius"].d <= r_max)
+        for name in fields:
+            fields[name] = unit_array(fields[name].d[mask], fields[name].units)
+        model = cls(int(mask.sum()), fields)
+        if "dm_df" in df:
+            model._dm_virial = VirialEquilibrium(model, ptype="dark_matter", df=df["dm_df"][mask])
+        if "star_df" in df:
+            model._star_virial = VirialEquilibrium(model, ptype="stellar", df=df["star_df"][mask])
+        return model
+
     # -- construction --------------------------------------------------------
     @classmethod
     def from_arrays(cls, fields):

@@ -15,7 +15,7 @@ from collections import OrderedDict, defaultdict
 
 import torch
 
-from .utils import ensure_list
+from .utils import _M_PER_KPC, _SEC_PER_MYR, ensure_list
 
 FIELD_UNITS = {
     "particle_position": "kpc",
@@ -25,6 +25,84 @@ FIELD_UNITS = {
     "thermal_energy": "kpc**2/Myr**2",
     "density": "Msun/kpc**3",
 }
+
+# Gadget-HDF5 naming (particles.py:13-75)
+gadget_fields = {
+    "dm": ["Coordinates", "Velocities", "Masses", "ParticleIDs", "Potential"],
+    "gas": ["Coordinates", "Velocities", "Masses", "ParticleIDs", "InternalEnergy", "MagneticField",
+            "Density", "Potential"],
+    "star": ["Coordinates", "Velocities", "Masses", "ParticleIDs", "Potential"],
+    "black_hole": ["Coordinates", "Velocities", "Masses", "ParticleIDs"],
+    "tracer": ["Coordinates"],
+}
+gadget_field_map = {
+    "Coordinates": "particle_position", "Velocities": "particle_velocity", "Masses": "particle_mass",
+    "Density": "density", "Potential": "potential_energy", "InternalEnergy": "thermal_energy",
+    "MagneticField": "magnetic_field", "Metallicity": "metallicity", "GFM_Metallicity": "metallicity",
+}
+gadget_field_units = {
+    "Coordinates": "kpc", "Velocities": "km/s", "Masses": "1e10*Msun", "Density": "1e10*Msun/kpc**3",
+    "InternalEnergy": "km**2/s**2", "Potential": "km**2/s**2", "PassiveScalars": "",
+    "MagneticField": "1e5*sqrt(Msun)*km/s/(kpc**1.5)", "Metallicity": "", "GFM_Metallicity": "",
+}
+code_fields = {"arepo": {"gas": ["PassiveScalars", "GFM_Metallicity"]}}
+ptype_map = OrderedDict([("PartType0", "gas"), ("PartType1", "dm"), ("PartType2", "tracer"),
+                         ("PartType4", "star"), ("PartType5", "black_hole")])
+rptype_map = OrderedDict([(v, k) for k, v in ptype_map.items()])
+
+#: km/s per kpc/Myr, from the same kpc and Julian-year definitions as utils.G
+KMS_PER_KPCMYR = _M_PER_KPC / 1.0e3 / _SEC_PER_MYR
+
+# unit string -> factor to the galactic base (kpc, Msun, Myr); the strings this package and the
+# Gadget layout use (the reference resolves arbitrary strings through unyt).  sqrt(Msun)*kpc**-0.5/Myr
+# is the galactic base of the magnetic-field unit.
+_GALACTIC = {
+    "": 1.0, "dimensionless": 1.0, "kpc": 1.0, "kpc/Myr": 1.0, "Msun": 1.0, "kpc**2/Myr**2": 1.0,
+    "Msun/kpc**3": 1.0, "Myr": 1.0, "sqrt(Msun)/(sqrt(kpc)*Myr)": 1.0,
+    "km/s": 1.0 / KMS_PER_KPCMYR, "1e10*Msun": 1.0e10, "1e10*Msun/kpc**3": 1.0e10,
+    "km**2/s**2": 1.0 / KMS_PER_KPCMYR**2,
+    "1e5*sqrt(Msun)*km/s/(kpc**1.5)": 1.0e5 / KMS_PER_KPCMYR,
+}
+_GALACTIC_NAME = {
+    "km/s": "kpc/Myr", "1e10*Msun": "Msun", "1e10*Msun/kpc**3": "Msun/kpc**3", "km**2/s**2": "kpc**2/Myr**2",
+    "1e5*sqrt(Msun)*km/s/(kpc**1.5)": "sqrt(Msun)/(sqrt(kpc)*Myr)", "dimensionless": "",
+}
+
+
+def _to_galactic(unit: str) -> float:
+    """Multiplier taking values in ``unit`` to kpc/Msun/Myr (``in_base("galactic")``)."""
+    try:
+        return _GALACTIC[unit.strip()]
+    except KeyError:
+        raise ValueError(f"unit {unit!r} is not one this package can convert "
+                         f"(known: {sorted(_GALACTIC)})") from None
+
+
+def _galactic_units(unit: str) -> str:
+    return _GALACTIC_NAME.get(unit.strip(), unit.strip())
+
+
+# galactic base -> Gadget unit, as direct factors (not reciprocals of _GALACTIC, so that a field
+# already in galactic units is scaled by exactly KMS_PER_KPCMYR, 1e-10, ...)
+_FROM_GALACTIC = {
+    "": 1.0, "kpc": 1.0, "km/s": KMS_PER_KPCMYR, "1e10*Msun": 1.0e-10, "1e10*Msun/kpc**3": 1.0e-10,
+    "km**2/s**2": KMS_PER_KPCMYR**2, "1e5*sqrt(Msun)*km/s/(kpc**1.5)": KMS_PER_KPCMYR * 1.0e-5,
+}
+
+
+def gadget_unit_scale(gadget_field: str, units: str) -> float:
+    """Multiplier from a field held in ``units`` to the Gadget unit of ``gadget_field``
+    (``fd.to(units)`` at particles.py:470-471)."""
+    return _to_galactic(units) * _FROM_GALACTIC[gadget_field_units[gadget_field]]
+
+
+def _to_device_planes(a, device) -> torch.Tensor:
+    """Host array -> device tensor; (n, k) arrays get plane-major (k, n) storage."""
+    import numpy as np
+
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    return t.T.contiguous().T if t.dim() == 2 else t
+
 
 
 class ClusterParticles:
@@ -143,23 +221,46 @@ class ClusterParticles:
         self._update_field_names()
 
     # -- persistence ------------------------------------------------------------
-    # The reference writes HDF5 (group per ptype, dataset per field, "units" attribute,
-    # particles.py:337-363).  There is no HDF5 library in this environment, so the same
-    # layout is stored in a NumPy .npz archive: key "<ptype>/<field>", plus "<ptype>/<field>.units".
+    # Same on-disk layouts as the reference (HDF5 via h5py there, via the native cgb_h5_*
+    # writer/reader of libcgb200 here; see include/cgb200.h and h5io.py).  Device fields
+    # stream to the file through pinned staging slots; no whole-field host copy is made.
+    def _clip_to_box(self, ptype, box_size):
+        """particles.py:105-107: mask of particles inside [0, box_size]^3."""
+        pos = self.fields[ptype, "particle_position"]
+        return ~((pos < 0.0).any(dim=1) | (pos > box_size).any(dim=1))
+
     def write_particles(self, output_filename, overwrite=False):
-        """Write the particles to ``output_filename`` (.npz; see the note above)."""
+        """Write the particles to an HDF5 file: one group per particle type, one dataset per
+        field, ``units`` string attribute on each (particles.py:337-363 + unyt ``write_hdf5``).
+        A file name ending in ``.npz`` selects a NumPy archive with the same keys instead."""
         import os
 
-        import numpy as np
-
         output_filename = str(output_filename)
-        if output_filename.endswith((".h5", ".hdf5")):
-            raise NotImplementedError("HDF5 output needs an HDF5 library, which is not available here; "
-                                      "use a .npz file name")
-        if not output_filename.endswith(".npz"):
-            output_filename += ".npz"
         if os.path.exists(output_filename) and not overwrite:
             raise IOError(f"Cannot create {output_filename}. It exists and overwrite=False.")
+        if output_filename.endswith(".npz"):
+            return self._write_npz(output_filename)
+        from .h5io import H5Writer
+
+        with H5Writer(output_filename, overwrite=True) as f:
+            for ptype in self.particle_types:
+                f.create_group(f"/{ptype}")
+            for (ptype, name), t in self.fields.items():
+                path = f"/{ptype}/{name}"
+                if t.is_cuda and t.dtype in (torch.float32, torch.float64):
+                    f.write_device(path, t, out_dtype=str(t.dtype).split(".")[1])
+                else:
+                    f.write(path, t.detach().cpu().numpy())
+                if name != "particle_index":
+                    f.set_attr(path, "units", self.field_units.get((ptype, name), ""))
+        return output_filename
+
+    def write_particles_to_h5(self, output_filename, overwrite=False):
+        return self.write_particles(output_filename, overwrite=overwrite)
+
+    def _write_npz(self, output_filename):
+        import numpy as np
+
         data = {}
         for (ptype, name), t in self.fields.items():
             data[f"{ptype}/{name}"] = t.detach().cpu().numpy()
@@ -169,11 +270,46 @@ class ClusterParticles:
 
     @classmethod
     def from_file(cls, filename, ptypes=None, device=None):
-        """Read particles written by :meth:`write_particles` (particles.py:235-274)."""
+        """Read particles written by :meth:`write_particles` or by the reference's
+        ``write_particles`` (particles.py:235-274).  Floating-point fields come back as
+        float64 in galactic units (kpc, Msun, Myr), as there."""
         import numpy as np
 
         device = device or ("cuda" if torch.cuda.is_available() else "cpu")
-        z = np.load(str(filename))
+        filename = str(filename)
+        with open(filename, "rb") as fh:
+            magic = fh.read(4)
+        if magic[:2] == b"PK":
+            return cls._from_npz(filename, ptypes, device)
+        from .h5io import H5Reader
+
+        fields = OrderedDict()
+        units = {}
+        with H5Reader(filename) as f:
+            all_ptypes = [k for k in f.keys("/") if f.is_group("/", k)]
+            ptypes = all_ptypes if ptypes is None else ensure_list(ptypes)
+            for ptype in ptypes:
+                for name in f.keys(f"/{ptype}"):
+                    path = f"/{ptype}/{name}"
+                    a = f.read(path)
+                    if name != "particle_index":
+                        unit = f.attrs(path).get("units", FIELD_UNITS.get(name, ""))
+                        a = a.astype(np.float64) * _to_galactic(unit)
+                        units[ptype, name] = _galactic_units(unit)
+                    fields[ptype, name] = _to_device_planes(a, device)
+        out = cls(ptypes, fields)
+        out.field_units.update(units)
+        return out
+
+    @classmethod
+    def from_h5_file(cls, filename, ptypes=None, device=None):
+        return cls.from_file(filename, ptypes=ptypes, device=device)
+
+    @classmethod
+    def _from_npz(cls, filename, ptypes, device):
+        import numpy as np
+
+        z = np.load(filename)
         keys = [k for k in z.files if not k.endswith(".units")]
         all_ptypes = list(dict.fromkeys(k.split("/")[0] for k in keys))
         ptypes = all_ptypes if ptypes is None else ensure_list(ptypes)
@@ -183,12 +319,121 @@ class ClusterParticles:
             ptype, name = k.split("/", 1)
             if ptype not in ptypes:
                 continue
-            a = torch.from_numpy(z[k]).to(device)
-            fields[ptype, name] = a.T.contiguous().T if a.dim() == 2 else a   # plane-major storage
+            fields[ptype, name] = _to_device_planes(z[k], device)
             units[ptype, name] = str(z[k + ".units"]) if k + ".units" in z.files else ""
         out = cls(ptypes, fields)
         out.field_units.update(units)
         return out
+
+    def write_to_gadget_file(self, ic_filename, box_size, dtype="float32", overwrite=False, code=None):
+        """Write Gadget-HDF5 initial conditions (particles.py:453-552): ``PartType{0,1,2,4,5}``
+        groups with Coordinates [kpc], Velocities [km/s], Masses [1e10 Msun], Density,
+        InternalEnergy / Potential [km**2/s**2], sequential uint32 ParticleIDs, particles
+        outside ``[0, box_size]^3`` dropped, and the ``Header`` attributes Gadget-family
+        codes read.  ``code="arepo"`` adds the ``Config`` group."""
+        import os
+
+        import numpy as np
+
+        from .h5io import H5Writer
+
+        ic_filename = str(ic_filename)
+        if os.path.exists(ic_filename) and not overwrite:
+            raise IOError(f"Cannot create {ic_filename}. It exists and overwrite=False.")
+        if np.dtype(dtype) not in (np.dtype("float32"), np.dtype("float64")):
+            raise ValueError("dtype must be 'float32' or 'float64'")
+        num_particles = {}
+        npart = 0
+        mass_table = np.zeros(6)
+        with H5Writer(ic_filename, overwrite=True) as f:
+            for ptype in self.particle_types:
+                gptype = rptype_map[ptype]
+                idxs = self._clip_to_box(ptype, box_size)
+                n_in = int(idxs.sum().item())
+                keep_all = n_in == idxs.numel()
+                num_particles[ptype] = n_in
+                f.create_group(f"/{gptype}")
+                for field in gadget_fields[ptype] + code_fields.get(code, {}).get(ptype, []):
+                    if field == "ParticleIDs":
+                        continue
+                    if field == "PassiveScalars":
+                        if self.num_passive_scalars > 0:
+                            data = torch.stack([self.fields[ptype, s] for s in self.passive_scalars], dim=-1)
+                            data = data if keep_all else data[idxs]
+                            f.write(f"/{gptype}/PassiveScalars", data.detach().cpu().numpy())
+                        continue
+                    my_field = gadget_field_map[field]
+                    if (ptype, my_field) not in self.fields:
+                        continue
+                    scale = gadget_unit_scale(field, self.field_units.get((ptype, my_field), ""))
+                    fd = self.fields[ptype, my_field]
+                    fd = fd if keep_all else fd[idxs]
+                    if fd.is_cuda:
+                        f.write_device(f"/{gptype}/{field}", fd, out_dtype=dtype, scale=scale)
+                    else:
+                        f.write(f"/{gptype}/{field}", (fd.double().numpy() * scale).astype(dtype))
+                    if field == "Masses" and ptype in ("star", "dm", "black_hole") and n_in:
+                        m0 = np.asarray(float(fd[0].item()) * scale).astype(dtype)
+                        mass_table[int(gptype[-1])] = m0
+                ids = np.arange(n_in, dtype=np.int64) + 1 + npart
+                f.write(f"/{gptype}/ParticleIDs", ids.astype("uint32"))
+                npart += n_in
+            f.create_group("/Header")
+            nums = np.array([num_particles.get("gas", 0), num_particles.get("dm", 0),
+                             num_particles.get("tracer", 0), 0, num_particles.get("star", 0),
+                             num_particles.get("black_hole", 0)], dtype="uint32")
+            header = [("Time", 0.0), ("Redshift", 0.0), ("BoxSize", float(box_size)), ("Omega0", 0.0),
+                      ("OmegaLambda", 0.0), ("HubbleParam", 1.0), ("NumPart_ThisFile", nums),
+                      ("NumPart_Total", nums), ("NumPart_Total_HighWord", np.zeros(6, dtype="uint32")),
+                      ("NumFilesPerSnapshot", 1), ("MassTable", mass_table), ("Flag_Sfr", 0),
+                      ("Flag_Cooling", 0), ("Flag_StellarAge", 0), ("Flag_Metals", 0), ("Flag_Feedback", 0),
+                      ("Flag_DoublePrecision", 0), ("Flag_IC_Info", 0)]
+            for k, v in header:
+                f.set_attr("/Header", k, v)
+            if code == "arepo":
+                f.create_group("/Config")
+                f.set_attr("/Config", "VORONOI", 1)
+        return ic_filename
+
+    @property
+    def num_passive_scalars(self):
+        return len(self.passive_scalars)
+
+    @classmethod
+    def from_gadget_file(cls, filename, ptypes=None, device=None):
+        """Read a Gadget-HDF5 snapshot / IC file into galactic units (particles.py:280-335);
+        a missing ``Masses`` dataset is filled from ``Header.MassTable``."""
+        import numpy as np
+
+        from .h5io import H5Reader
+
+        device = device or ("cuda" if torch.cuda.is_available() else "cpu")
+        fields = OrderedDict()
+        particle_types = []
+        with H5Reader(str(filename)) as f:
+            if ptypes is None:
+                gptypes = [k for k in f.keys("/") if k.startswith("PartType")]
+            else:
+                gptypes = [rptype_map[k] for k in ensure_list(ptypes)]
+            for gptype in gptypes:
+                my_ptype = ptype_map[gptype]
+                particle_types.append(my_ptype)
+                present = f.keys(f"/{gptype}")
+                for field in gadget_fields[my_ptype]:
+                    if field not in present:
+                        continue
+                    a = f.read(f"/{gptype}/{field}")
+                    if field == "ParticleIDs":
+                        fields[my_ptype, "particle_index"] = torch.from_numpy(a.astype(np.int64)).to(device)
+                    else:
+                        a = a.astype(np.float64) * _to_galactic(gadget_field_units[field])
+                        fields[my_ptype, gadget_field_map[field]] = _to_device_planes(a, device)
+                if "Masses" not in present:
+                    n_ptype = f.info(f"/{gptype}/ParticleIDs")[1][0]
+                    m = float(f.attrs("/Header")["MassTable"][int(gptype[-1])])
+                    fields[my_ptype, "particle_mass"] = torch.full(
+                        (n_ptype,), m * _to_galactic(gadget_field_units["Masses"]), dtype=torch.float64, device=device)
+        return cls(particle_types, fields)
 
     def to_numpy(self):
         """Host copy: dict (ptype, field) -> ndarray."""

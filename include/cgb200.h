@@ -46,6 +46,7 @@ extern "C" {
 #define CGB_E_WORKSPACE (-3) /* workspace too small / misaligned                       */
 #define CGB_E_NOTMONO (-4)   /* abscissa not strictly increasing ("x must be increasing",
                                 what InterpolatedUnivariateSpline raises at virial.py:45) */
+#define CGB_E_IO (-5)        /* file could not be created / read / parsed (IOError)      */
 
 #define CGB_STREAM_RADIUS 0u
 #define CGB_STREAM_POS_DIR 1u
@@ -293,6 +294,62 @@ int cgb_resample_gas(const cgb_halo_tables *halos, int num_halos, const void *d_
 int cgb_map_field(const double *d_gx, const double *d_gy, const double *d_gz, int nx, int ny, int nz,
                   const double *d_fx, const double *d_fy, const double *d_fz, const void *d_pos,
                   int64_t ld, int64_t n, int dtype, void *d_out, void *stream);
+
+/* ------------------------------------------------------------------------ */
+/* Particle files ("next" row 2): a native writer/reader for the HDF5 subset the reference's
+ * particle files use -- h5py/libhdf5 do the same job there:
+ *   ClusterParticles.write_particles / from_file            (particles.py:239-274, 337-363):
+ *       group per particle type, dataset per field, "units" string attribute (unyt write_hdf5)
+ *   ClusterParticles.write_to_gadget_file / from_gadget_file (particles.py:280-335, 453-552):
+ *       PartType{0,1,2,4,5} groups, Header group attributes
+ * Layout written: superblock v0, symbol-table groups, v1 object headers, contiguous
+ * little-endian datasets, variable-length UTF-8 string attributes -- what h5py writes with its
+ * default libver, so either side reads the other's files.  Host-only except
+ * cgb_h5_write_dataset_device.  Object paths are '/'-separated; parents must exist.  Handles
+ * are not thread-safe.  Errors: CGB_E_IO (file), CGB_E_INVALID (argument). */
+#define CGB_H5_F32 1
+#define CGB_H5_F64 2
+#define CGB_H5_I32 3
+#define CGB_H5_U32 4
+#define CGB_H5_I64 5
+#define CGB_H5_U64 6
+#define CGB_H5_STR 7 /* attributes only: scalar string (NUL-terminated char* in, bytes out) */
+
+typedef struct cgb_h5_file cgb_h5_file;
+
+int cgb_h5_create(const char *path, int overwrite, cgb_h5_file **out);
+int cgb_h5_create_group(cgb_h5_file *f, const char *path);
+/* host_data: C-ordered dims[0..rank) elements of dtype; rank 0..4 (0 = scalar dataset) */
+int cgb_h5_write_dataset(cgb_h5_file *f, const char *path, int dtype, int rank, const int64_t *dims,
+                         const void *host_data);
+/* d_src: (ncomp, ld) device planes of src_dtype (f32/f64).  Written as an (n, ncomp) dataset
+ * ((n,) if ncomp == 1) of out_dtype with value (out_dtype)((double)x * scale) -- the unit
+ * conversion and cast of particles.py:470-472.  Pack kernel + D2H of chunk k+1 overlap the file
+ * write of chunk k (two pinned 32 MiB slots owned by the handle).  Returns after the data is
+ * in the file. */
+int cgb_h5_write_dataset_device(cgb_h5_file *f, const char *path, int out_dtype, const void *d_src,
+                                int src_dtype, int64_t n, int ncomp, int64_t ld, double scale,
+                                void *stream);
+/* count < 0: scalar; count >= 0: 1-D array of count elements.  CGB_H5_STR: data = char*. */
+int cgb_h5_set_attr(cgb_h5_file *f, const char *obj_path, const char *name, int dtype, int64_t count,
+                    const void *data);
+/* writer: lays out the metadata, writes the superblock, frees the handle (also on error) */
+int cgb_h5_close(cgb_h5_file *f);
+
+int cgb_h5_open(const char *path, cgb_h5_file **out);
+int cgb_h5_num_children(cgb_h5_file *f, const char *group_path, int *n);
+int cgb_h5_child_name(cgb_h5_file *f, const char *group_path, int i, char *buf, int buflen,
+                      int *is_group);
+/* file_offset: absolute byte offset of the contiguous data (-1 for compact / empty datasets) */
+int cgb_h5_dataset_info(cgb_h5_file *f, const char *path, int *dtype, int *rank, int64_t *dims4,
+                        int64_t *file_offset);
+int cgb_h5_read_dataset(cgb_h5_file *f, const char *path, void *host_out, size_t bytes);
+int cgb_h5_num_attrs(cgb_h5_file *f, const char *obj_path, int *n);
+int cgb_h5_attr_name(cgb_h5_file *f, const char *obj_path, int i, char *buf, int buflen);
+/* dtype 0 = attribute exists but its type is outside the subset; bytes = payload size */
+int cgb_h5_attr_info(cgb_h5_file *f, const char *obj_path, const char *name, int *dtype,
+                     int64_t *count, size_t *bytes);
+int cgb_h5_read_attr(cgb_h5_file *f, const char *obj_path, const char *name, void *out, size_t bytes);
 
 #ifdef __cplusplus
 }

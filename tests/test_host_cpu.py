@@ -207,26 +207,6 @@ def test_radial_cut_and_black_hole():
     assert p["black_hole", "particle_mass"].tolist() == [1.0e9, 2.0e9]
 
 
-def test_write_and_read_particles_round_trip(tmp_path):
-    """particles.py:235-274, 337-363 semantics (npz container instead of HDF5)."""
-    from cluster_generator_b200 import ClusterParticles
-
-    pos = torch.arange(30, dtype=torch.float64).reshape(3, 10)
-    p = ClusterParticles("dm", {("dm", "particle_position"): pos.T, ("dm", "particle_velocity"): (2 * pos).T,
-                                ("dm", "particle_mass"): torch.ones(10, dtype=torch.float64)})
-    fn = p.write_particles(str(tmp_path / "parts"))
-    with pytest.raises(IOError):
-        p.write_particles(fn)
-    p.write_particles(fn, overwrite=True)
-    with pytest.raises(NotImplementedError):
-        p.write_particles(str(tmp_path / "parts.h5"))
-    q = ClusterParticles.from_file(fn, device="cpu")
-    assert q.num_particles == {"dm": 10} and q.field_units["dm", "particle_velocity"] == "kpc/Myr"
-    for k in p.fields:
-        assert torch.equal(q[k], p[k])
-    assert q["dm", "particle_position"].T.is_contiguous()
-
-
 def test_radial_profile_algebra():
     """cluster_generator/tests/test_radial_profiles.py:100-123"""
     import cluster_generator_b200 as cg
@@ -323,7 +303,7 @@ def test_cluster_ics_particle_budget_split():
                         num_particles={"dm": 1_000_000}, r_max=5000.0)
     assert ics.num_particles["dm"] == [750_000, 250_000]
     assert ics.num_particles["gas"] == [0, 0] and ics.num_particles["star"] == [0, 0]
-    with pytest.raises(NotImplementedError):
-        cg.ClusterICs("m", 1, ["model.h5"], [0, 0, 0], [0, 0, 0])
+    with pytest.raises(IOError, match="Cannot open"):      # profiles may be model files (ics.py:104)
+        cg.ClusterICs("m", 1, ["absent_model.h5"], [0, 0, 0], [0, 0, 0])
     with pytest.raises(ValueError):
         cg.ClusterICs("m", 2, [big], [[0, 0, 0]] * 2, [[0, 0, 0]] * 2)

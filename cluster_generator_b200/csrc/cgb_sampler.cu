@@ -456,6 +456,41 @@ __device__ __forceinline__ float screen_es(double psi, double vesc, double env, 
     return es;
 }
 
+// (-1)^k (pi/2)^(2k+1) / (2k+1)!  and  (-1)^k (pi/2)^(2k) / (2k)!, correctly rounded
+__constant__ double SC2PI_SIN[9] = {0x1.921fb54442d18p+0,  -0x1.4abbce625be53p-1, 0x1.466bc6775aae2p-4,
+                                    -0x1.32d2cce62bd86p-8, 0x1.50783487ee782p-13, -0x1.e3074fde8871fp-19,
+                                    0x1.e8f434d018d63p-25, -0x1.6fadb9f155744p-31, 0x1.aaec32af93359p-38};
+__constant__ double SC2PI_COS[9] = {1.0,                   -0x1.3bd3cc9be45dep+0, 0x1.03c1f081b5ac4p-2,
+                                    -0x1.55d3c7e3cbffap-6, 0x1.e1f506891babbp-11, -0x1.a6d1f2a204a8cp-16,
+                                    0x1.f9d38a3763cc3p-22, -0x1.b6e24f44b128fp-28, 0x1.20c62c2f2d7f5p-34};
+
+// sin(2 pi u), cos(2 pi u) for u in [0, 1) (virial.py:176,180-182: phi = 2 pi u).  The quadrant
+// reduction r = 4u - rint(4u) is exact; sin/cos(pi/2 r) on |r| <= 1/2 are Taylor polynomials
+// whose truncation error is < 3e-18 relative, so the result is within ~1 ulp like sincospi(2u),
+// at under half its instruction count (no general-argument, huge-argument or NaN paths).
+__device__ __forceinline__ void sincos2pi(double u, double* sn, double* cs)
+{
+    const double t = __dmul_rn(u, 4.0);
+    const double big = __dadd_rn(t, 6755399441055744.0);  // 1.5 * 2^52: low word holds rint(t)
+    const int q = __double2loint(big);
+    const double r = __dsub_rn(t, __dsub_rn(big, 6755399441055744.0));
+    const double x = __dmul_rn(r, r);
+    // coefficients come from the constant bank: DFMA takes c[][] operands directly, while
+    // 64-bit immediates would each cost two uniform moves
+    double ps = SC2PI_SIN[8];
+#pragma unroll
+    for (int k = 7; k >= 0; --k) ps = fma(ps, x, SC2PI_SIN[k]);
+    ps = __dmul_rn(ps, r);
+    double pc = SC2PI_COS[8];
+#pragma unroll
+    for (int k = 7; k >= 0; --k) pc = fma(pc, x, SC2PI_COS[k]);
+    const bool odd = q & 1;  // quadrants 1, 3: sin <- cos, cos <- sin
+    const double s = odd ? pc : ps, c = odd ? ps : pc;
+    // sin < 0 in quadrants 2, 3; cos < 0 in quadrants 1, 2 (sign bit of the high word)
+    *sn = __hiloint2double(__double2hiint(s) ^ ((q & 2) << 30), __double2loint(s));
+    *cs = __hiloint2double(__double2hiint(c) ^ (((q + 1) & 2) << 30), __double2loint(c));
+}
+
 // fp32 screen: 0 = reject, 1 = accept, 2 = undecided.
 __device__ __forceinline__ int screen_trial(const float2* __restrict__ s_screen, float inv_w_f,
                                             unsigned wa, unsigned wb, float ps, float vs, float es)
@@ -683,13 +718,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
             const double ct = __dadd_rn(-1.0, __dmul_rn(2.0, uc));
             const double st = sqrt(__dmul_rn(__dsub_rn(1.0, ct), __dadd_rn(1.0, ct)));
             double sp, cp;
-            sincospi(__dmul_rn(2.0, up), &sp, &cp);
+            sincos2pi(up, &sp, &cp);
             const double rs = __dmul_rn(r, st);
             const double px = __dmul_rn(rs, cp), py = __dmul_rn(rs, sp), pz = __dmul_rn(r, ct);
             const double ctv = __dadd_rn(-1.0, __dmul_rn(2.0, ucv));
             const double stv = sqrt(__dmul_rn(__dsub_rn(1.0, ctv), __dadd_rn(1.0, ctv)));
             double spv, cpv;
-            sincospi(__dmul_rn(2.0, upv), &spv, &cpv);
+            sincos2pi(upv, &spv, &cpv);
             const double vsn = __dmul_rn(v, stv);
             const double vx = __dmul_rn(vsn, cpv), vy = __dmul_rn(vsn, spv), vz = __dmul_rn(v, ctv);
             store_out<OutT>(p.pos, loc, px);
@@ -1066,7 +1101,7 @@ __global__ void __launch_bounds__(512, 1) cgb_hard_kernel(const __grid_constant_
             const double ctv = __dadd_rn(-1.0, __dmul_rn(2.0, ucv));
             const double stv = sqrt(__dmul_rn(__dsub_rn(1.0, ctv), __dadd_rn(1.0, ctv)));
             double spv, cpv;
-            sincospi(__dmul_rn(2.0, upv), &spv, &cpv);
+            sincos2pi(upv, &spv, &cpv);
             const double vsn = __dmul_rn(v, stv);
             const double vx = __dmul_rn(vsn, cpv), vy = __dmul_rn(vsn, spv), vz = __dmul_rn(v, ctv);
             store_out<OutT>(p.vel, loc, vx);
@@ -1167,7 +1202,7 @@ __global__ void __launch_bounds__(256) cgb_gas_kernel(const __grid_constant__ Sa
         const double ct = __dadd_rn(-1.0, __dmul_rn(2.0, uc));
         const double st = sqrt(__dmul_rn(__dsub_rn(1.0, ct), __dadd_rn(1.0, ct)));
         double sp, cp;
-        sincospi(__dmul_rn(2.0, up), &sp, &cp);
+        sincos2pi(up, &sp, &cp);
         const double rs = __dmul_rn(r, st);
         store_out<OutT>(p.pos, loc, __dmul_rn(rs, cp));
         store_out<OutT>(p.pos, p.ld + loc, __dmul_rn(rs, sp));
@@ -1219,7 +1254,7 @@ cgb_assemble_kernel(SampleParams p, const double* __restrict__ r_sub, const doub
         const double ct = __dadd_rn(-1.0, __dmul_rn(2.0, uc));
         const double st = sqrt(__dmul_rn(__dsub_rn(1.0, ct), __dadd_rn(1.0, ct)));
         double sp, cp;
-        sincospi(__dmul_rn(2.0, up), &sp, &cp);
+        sincos2pi(up, &sp, &cp);
         const double rs = __dmul_rn(r, st);
         store_out<OutT>(p.pos, loc, __dmul_rn(rs, cp));
         store_out<OutT>(p.pos, p.ld + loc, __dmul_rn(rs, sp));
@@ -1227,7 +1262,7 @@ cgb_assemble_kernel(SampleParams p, const double* __restrict__ r_sub, const doub
         const double ctv = __dadd_rn(-1.0, __dmul_rn(2.0, ucv));
         const double stv = sqrt(__dmul_rn(__dsub_rn(1.0, ctv), __dadd_rn(1.0, ctv)));
         double spv, cpv;
-        sincospi(__dmul_rn(2.0, upv), &spv, &cpv);
+        sincos2pi(upv, &spv, &cpv);
         const double vsn = __dmul_rn(v, stv);
         store_out<OutT>(p.vel, loc, __dmul_rn(vsn, cpv));
         store_out<OutT>(p.vel, p.ld + loc, __dmul_rn(vsn, spv));

@@ -41,9 +41,10 @@ keys = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'la
         'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio', 'smsp__warps_eligible.avg.per_cycle_active']
-o2 = [f"# ncu --set full, {tag} (`-k regex:cgb_sample_kernel|cgb_gas_kernel|cgb_eddington_g_kernel -s 4 -c 3`, bench.py --steps 3 --warmup 3)", "",
+o2 = [f"# ncu --set full, {tag} (`-k regex:cgb_sample_kernel|cgb_gas_kernel|cgb_eddington_g_kernel -c 10`, bench.py --steps 3 --warmup 3; last capture of each kernel)", "",
       "Raw report kept out of git (9 MB); regenerate with the command above. Values per launch, workload = bench.py (1e7 Vikhlinin DM / 1e7 gas).", ""]
-for row in r[2:]:
+last = collections.OrderedDict((row[h.index('Kernel Name')], row) for row in r[2:])  # one (the last) capture per kernel
+for row in last.values():
     o2 += [f"## {row[h.index('Kernel Name')]}", "", "| metric | value | unit |", "|---|---:|---|"]
     o2 += [f"| {k} | {row[h.index(k)]} | {units[h.index(k)]} |" for k in keys if k in h] + [""]
     print(row[h.index('Kernel Name')][:50], row[h.index('gpu__time_duration.sum')], row[h.index('dram__bytes_read.sum')],

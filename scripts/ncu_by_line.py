@@ -24,8 +24,9 @@ for l in sass[start + 1:]:
         continue
     if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l):
         lines.append(cur)
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout.splitlines()
-# take the first kernel block
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + re.sub(r"^_Z\d+|I.*$", "", kname)],
+                     capture_output=True, text=True).stdout.splitlines()
+# take the first matching kernel block
 hdr_i = next(i for i, l in enumerate(out) if l.startswith('"Address"'))
 rdr = csv.reader(out[hdr_i:])
 hdr = next(rdr)

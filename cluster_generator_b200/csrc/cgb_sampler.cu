@@ -35,6 +35,15 @@
 #include "cgb_spline.cuh"
 
 #define NB 4096            // screen buckets
+// Phase-1 shape, measured on B200 (1e7 Vikhlinin / Hernquist / NFW DM, 2e6 BCG stars, ms):
+//   1 pair/iteration 0.923 1.696 1.513 2.705 | 2: 0.882 1.551 1.373 2.640 | 3: 0.884 1.527 1.332 2.526
+//   3 + all screens up front 0.868 1.543 1.310 2.471 | 4: 0.906 1.620 1.344 2.508 | 4 + all 0.938 1.718 1.401 2.510
+#ifndef LEAN_PAIRS
+#define LEAN_PAIRS 3       // trial pairs (independent Philox chains) per lane per phase-1 iteration
+#endif
+#ifndef LEAN_SCREEN_ALL
+#define LEAN_SCREEN_ALL 1  // screen all 2*LEAN_PAIRS trials before looking at any result
+#endif
 #ifndef WARPS
 #define WARPS 16           // warps per CTA
 #endif
@@ -952,6 +961,96 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
             // ---- one Philox call = two trials for every active lane ----
             bool done_oth = false;
             if (slot >= 0) {
+#if LEAN_PAIRS >= 2
+                // LEAN_PAIRS independent Philox chains per iteration (trial pairs pair ..
+                // pair + LEAN_PAIRS - 1): more ILP and less loop overhead per trial; the later
+                // pairs' work is discarded when an earlier one accepts
+                const Philox4 w0 = philox_rk(p.rk, id_lo, id_hi, pair, CGB_STREAM_VEL_TRIAL);
+                const Philox4 w1 = philox_rk(p.rk, id_lo, id_hi, pair + 1u, CGB_STREAM_VEL_TRIAL);
+#if LEAN_PAIRS >= 3
+                const Philox4 w2 = philox_rk(p.rk, id_lo, id_hi, pair + 2u, CGB_STREAM_VEL_TRIAL);
+#endif
+#if LEAN_PAIRS >= 4
+                const Philox4 w3 = philox_rk(p.rk, id_lo, id_hi, pair + 3u, CGB_STREAM_VEL_TRIAL);
+#endif
+                int acc = 0;
+                unsigned wacc = 0, ntr = 0;
+#if LEAN_SCREEN_ALL
+                // screen every trial of the iteration up front (independent fp32 chains), then
+                // take the first accepted one; any undecided trial sends the lane to the
+                // sequential path below
+                const int t0 = screen_trial(s_screen, T.inv_w_f, w0.x, w0.y, ps, vs, es);
+                const int t1 = screen_trial(s_screen, T.inv_w_f, w0.z, w0.w, ps, vs, es);
+                const int t2 = screen_trial(s_screen, T.inv_w_f, w1.x, w1.y, ps, vs, es);
+                const int t3 = screen_trial(s_screen, T.inv_w_f, w1.z, w1.w, ps, vs, es);
+                int any = t0 | t1 | t2 | t3;
+#if LEAN_PAIRS >= 3
+                const int t4 = screen_trial(s_screen, T.inv_w_f, w2.x, w2.y, ps, vs, es);
+                const int t5 = screen_trial(s_screen, T.inv_w_f, w2.z, w2.w, ps, vs, es);
+                any |= t4 | t5;
+#endif
+#if LEAN_PAIRS >= 4
+                const int t6 = screen_trial(s_screen, T.inv_w_f, w3.x, w3.y, ps, vs, es);
+                const int t7 = screen_trial(s_screen, T.inv_w_f, w3.z, w3.w, ps, vs, es);
+                any |= t6 | t7;
+#endif
+                if (!(any & 2)) {
+                    if (any) {
+                        acc = 1;
+#if LEAN_PAIRS >= 4
+                        if (t7) { wacc = w3.z; ntr = 8u; }
+                        if (t6) { wacc = w3.x; ntr = 7u; }
+#endif
+#if LEAN_PAIRS >= 3
+                        if (t5) { wacc = w2.z; ntr = 6u; }
+                        if (t4) { wacc = w2.x; ntr = 5u; }
+#endif
+                        if (t3) { wacc = w1.z; ntr = 4u; }
+                        if (t2) { wacc = w1.x; ntr = 3u; }
+                        if (t1) { wacc = w0.z; ntr = 2u; }
+                        if (t0) { wacc = w0.x; ntr = 1u; }
+                        ntr += 2u * pair;
+                    }
+                } else
+#endif
+                {
+                    PairResult r = eval_pair(T, s_screen, w0, ps, vs, es, s_psi + slot, s_ves + slot, env_ptr(slot));
+                    m_exact += r.n_exact;
+                    wacc = (r.acc == 1) ? w0.x : w0.z;
+                    ntr = 2u * pair + (unsigned)r.acc;
+                    if (!r.acc) {
+                        r = eval_pair(T, s_screen, w1, ps, vs, es, s_psi + slot, s_ves + slot, env_ptr(slot));
+                        m_exact += r.n_exact;
+                        wacc = (r.acc == 1) ? w1.x : w1.z;
+                        ntr = 2u * pair + 2u + (unsigned)r.acc;
+#if LEAN_PAIRS >= 3
+                        if (!r.acc) {
+                            r = eval_pair(T, s_screen, w2, ps, vs, es, s_psi + slot, s_ves + slot, env_ptr(slot));
+                            m_exact += r.n_exact;
+                            wacc = (r.acc == 1) ? w2.x : w2.z;
+                            ntr = 2u * pair + 4u + (unsigned)r.acc;
+#if LEAN_PAIRS >= 4
+                            if (!r.acc) {
+                                r = eval_pair(T, s_screen, w3, ps, vs, es, s_psi + slot, s_ves + slot, env_ptr(slot));
+                                m_exact += r.n_exact;
+                                wacc = (r.acc == 1) ? w3.x : w3.z;
+                                ntr = 2u * pair + 6u + (unsigned)r.acc;
+                            }
+#endif
+                        }
+#endif
+                    }
+                    acc = r.acc;
+                }
+                if (acc) {
+                    s_wa[slot] = wacc;
+                    s_tri[slot] = (int)ntr;
+                    done_oth = (slot >= TILE) != (cur == 1);
+                    slot = -1;
+                } else {
+                    pair += (unsigned)LEAN_PAIRS;
+                }
+#else
                 const Philox4 w = philox_rk(p.rk, id_lo, id_hi, pair, CGB_STREAM_VEL_TRIAL);
                 const PairResult r = eval_pair(T, s_screen, w, ps, vs, es, s_psi + slot, s_ves + slot,
                                                env_ptr(slot));
@@ -964,6 +1063,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
                 } else {
                     ++pair;
                 }
+#endif
             }
             // particles of the older tile that just finished; the tile goes out when all did
             const unsigned dn = __ballot_sync(FULL, done_oth);

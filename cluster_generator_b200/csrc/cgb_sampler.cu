@@ -56,7 +56,7 @@
                            // (1e7 Vikhlinin DM): 2x128 1.06 ms, 3x96 1.13, 4x64 1.15, 4x96 1.19
 #define NBC 1024           // buckets of the CDF start-index table
 #ifndef LANE_CAP_PAIRS
-#define LANE_CAP_PAIRS 96  // trial pairs a particle may spend in its lane before the warp takes over
+#define LANE_CAP_PAIRS 384 // trial pairs a particle may spend in its lane before the warp takes over (48/96/192/384: Hernquist 1.47/1.56/1.45/1.45 ms, stars 2.57/2.55/2.43/2.41)
 #endif
 #define HARD_PAIRS 32768   // pair index beyond which a particle is deferred to the grid-wide pass
 #define HARD_CAP 4096      // capacity of the deferred-particle list

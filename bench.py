@@ -234,6 +234,7 @@ def run_cuda(args):
     import torch
     import torch.distributed as dist
 
+    import cluster_generator_b200 as cg
     from cluster_generator_b200 import _native as N
     from cluster_generator_b200.virial import SamplerTables
 
@@ -304,9 +305,33 @@ def run_cuda(args):
 
     k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
 
+    # The 16-word moment all-reduce is the path's only collective.  Default ("peer"): fused into
+    # the sampler kernel -- every rank's final flush adds its partial sums to all ranks' buffers
+    # over NVLink (cluster_generator_b200/peer.py), a fresh arena slot per step, nothing to wait
+    # for but the kernels themselves.  "nccl": dist.all_reduce per step, asynchronously into one
+    # of two buffers and drained before the closing event (the baseline this replaces).
+    mom_mode = os.environ.get("CGB_BENCH_MOMENTS", "peer") if world > 1 else "local"
+    if mom_mode not in ("peer", "nccl", "local"):
+        raise SystemExit("CGB_BENCH_MOMENTS must be peer or nccl")
+    peer = cg.PeerMoments(slots=args.steps + args.warmup + 8) if mom_mode == "peer" else None
+    mom_ring = [moments, torch.zeros_like(moments)]
+    pending = [None, None]
+    last = {"mom": moments}
+
     def step(i, timed_idx=None):
-        moments.zero_()
         a, g = dm_args(1000 + i), gas_args(5000 + i)
+        if peer is not None:
+            slot = peer.next_slot()
+            peer.attach(a, slot)
+            last["mom"] = peer.slot(slot)
+        else:
+            moments = mom_ring[i & 1]
+            if pending[i & 1] is not None:
+                pending[i & 1].wait()
+                pending[i & 1] = None
+            moments.zero_()
+            a.d_moments = moments.data_ptr()
+            last["mom"] = moments
         sp = N.stream_ptr()
         if timed_idx is not None:
             k_ev[timed_idx][0].record()
@@ -314,8 +339,14 @@ def run_cuda(args):
         if timed_idx is not None:
             k_ev[timed_idx][1].record()
         N.check(L.cgb_sample_gas(N.ctypes.byref(g), N.ptr(g_e), N.ptr(g_rho), sp))
-        if world > 1:
-            dist.all_reduce(moments)
+        if mom_mode == "nccl":
+            pending[i & 1] = dist.all_reduce(last["mom"], async_op=True)
+
+    def drain():
+        for k in (0, 1):
+            if pending[k] is not None:
+                pending[k].wait()
+                pending[k] = None
 
     def barrier():
         if world > 1:
@@ -324,6 +355,7 @@ def run_cuda(args):
 
     for i in range(args.warmup):
         step(i)
+    drain()
     barrier()
     clocks = ClockSampler(local)
     barrier()
@@ -333,12 +365,13 @@ def run_cuda(args):
     t0.record()
     for i in range(args.steps):
         step(args.warmup + i, i)
+    drain()
     t1.record()
     barrier()
     ms = t0.elapsed_time(t1)
     clk = clocks.stop() if rank == 0 else None
     k_ms = sum(a.elapsed_time(b) for a, b in k_ev) / args.steps
-    mom = moments.cpu().numpy()  # last step (all-reduced when world > 1)
+    mom = last["mom"].cpu().numpy()  # last step, summed over ranks when world > 1
     tt = torch.tensor([ms, k_ms], dtype=f64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)

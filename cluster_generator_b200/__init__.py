@@ -18,6 +18,7 @@ from .particles import (  # noqa: F401
     resample_three_clusters,
     resample_two_clusters,
 )
+from .peer import PeerMoments  # noqa: F401
 from .radial_profiles import (  # noqa: F401
     RadialProfile,
     hernquist_density_profile,

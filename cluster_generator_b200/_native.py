@@ -57,6 +57,7 @@ class SampleArgs(Structure):
         ("d_pos", c_void_p), ("d_vel", c_void_p), ("ld", c_int64), ("d_mass", c_void_p),
         ("d_pot", c_void_p), ("d_radius", c_void_p), ("d_speed", c_void_p), ("d_trials", c_void_p),
         ("d_moments", c_void_p), ("hu", HostUniforms), ("radius_period", c_int64),
+        ("n_peers", c_int32), ("pad_peers", c_int32), ("d_peer_moments", c_void_p * 8),
     ]
 
 
@@ -102,6 +103,10 @@ SYMBOLS = [
                               c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     ("cgb_resample_gas", c_int, [POINTER(HaloTables), c_int, c_void_p, c_int64, c_int64, c_int, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    ("cgb_peer_alloc", c_int, [c_size_t, POINTER(c_void_p), c_char_p]),
+    ("cgb_peer_open", c_int, [c_char_p, POINTER(c_void_p)]),
+    ("cgb_peer_close", c_int, [c_void_p]),
+    ("cgb_peer_free", c_int, [c_void_p]),
     ("cgb_h5_create", c_int, [c_char_p, c_int, POINTER(c_void_p)]),
     ("cgb_h5_create_group", c_int, [c_void_p, c_char_p]),
     ("cgb_h5_write_dataset", c_int, [c_void_p, c_char_p, c_int, c_int, POINTER(c_int64), c_void_p]),

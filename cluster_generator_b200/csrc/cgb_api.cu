@@ -86,3 +86,47 @@ extern "C" int cgb_measure_ffma_tflops(int iters, double* tflops, void* stream)
 {
     return measure_fma<float>(iters, tflops, stream);
 }
+
+// ---------------------------------------------------------------------------
+// peer-visible buffers (CUDA IPC) for the fused moment all-reduce
+// ---------------------------------------------------------------------------
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+
+extern "C" int cgb_peer_alloc(size_t bytes, void** d_ptr, unsigned char handle_out[64])
+{
+    CGB_REQUIRE(bytes > 0 && d_ptr && handle_out, "cgb_peer_alloc: bad argument");
+    void* p = nullptr;
+    CGB_CUDA_CHECK(cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        cgb_set_error("cgb_peer_alloc: %s", cudaGetErrorString(e));
+        return CGB_E_CUDA;
+    }
+    memcpy(handle_out, &h, 64);
+    *d_ptr = p;
+    return CGB_OK;
+}
+
+extern "C" int cgb_peer_open(const unsigned char handle[64], void** d_ptr)
+{
+    CGB_REQUIRE(handle && d_ptr, "cgb_peer_open: bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CGB_CUDA_CHECK(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return CGB_OK;
+}
+
+extern "C" int cgb_peer_close(void* d_ptr)
+{
+    if (d_ptr) CGB_CUDA_CHECK(cudaIpcCloseMemHandle(d_ptr));
+    return CGB_OK;
+}
+
+extern "C" int cgb_peer_free(void* d_ptr)
+{
+    if (d_ptr) CGB_CUDA_CHECK(cudaFree(d_ptr));
+    return CGB_OK;
+}

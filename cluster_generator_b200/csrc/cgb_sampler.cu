@@ -345,7 +345,31 @@ struct SampleParams {
     const double* in_psi; const double* in_vesc; const double* in_env;
     long long first_id;
     long long radius_period;  // gas sub_sample: radius of id taken from id % radius_period
+    // n_peers > 0: the moments go to every rank's buffer (peer-mapped over NVLink) instead of
+    // `moments` alone -- the all-reduce of the path, fused into the kernels' final flush
+    int n_peers;
+    double* peer_moments[CGB_MAX_PEERS];
 };
+
+__device__ __forceinline__ void mom_add(const SampleParams& p, int k, double v)
+{
+    if (p.n_peers > 0) {
+        for (int r = 0; r < p.n_peers; ++r) atomicAdd_system(p.peer_moments[r] + k, v);
+    } else {
+        atomicAdd(p.moments + k, v);
+    }
+}
+
+// max via integer atomicMax on the bits (non-negative doubles order like integers)
+__device__ __forceinline__ void mom_max(const SampleParams& p, int k, double v)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    if (p.n_peers > 0) {
+        for (int r = 0; r < p.n_peers; ++r) atomicMax_system((unsigned long long*)(p.peer_moments[r] + k), b);
+    } else {
+        atomicMax((unsigned long long*)(p.moments + k), b);
+    }
+}
 
 // Philox4x32-10 with the key schedule taken from the kernel parameters
 __device__ __forceinline__ Philox4 philox_rk(const unsigned (&rk)[20], unsigned c0, unsigned c1,
@@ -1083,6 +1107,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
     }
 
     // ---------------- moments ----------------
+    // per-warp partial sums (shared memory) -> one CTA total -> one flush per CTA; with peers
+    // the flush goes to every rank's buffer over NVLink, so it is kept to 16 words per CTA
     if (p.moments) {
         unsigned long long ex = m_exact;
         for (int o = 16; o; o >>= 1) ex += __shfl_xor_sync(FULL, ex, o);
@@ -1091,14 +1117,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
             s_mom[12] = (double)m_coop;
             s_mom[15] = (double)ex;
         }
-        __syncwarp();
-        if (lane < CGB_NMOMENTS && lane != 2) {
-            const double v = s_mom[lane];
-            if (v != 0.0) atomicAdd(p.moments + lane, v);
-        }
+    }
+    __syncthreads();
+    if (p.moments && warp == 0 && lane < CGB_NMOMENTS) {
+        const double* all = (const double*)(smem + SCREEN_BYTES + (size_t)WARPS * (NBUF * TILE) * 32);
+        double v = 0.0;
         if (lane == 2) {
-            // max via integer atomicMax on the bits (non-negative doubles order like integers)
-            atomicMax((unsigned long long*)(p.moments + 2), (unsigned long long)__double_as_longlong(s_mom[2]));
+            for (int w = 0; w < WARPS; ++w) v = fmax(v, all[w * CGB_NMOMENTS + 2]);
+            mom_max(p, 2, v);
+        } else {
+            for (int w = 0; w < WARPS; ++w) v += all[w * CGB_NMOMENTS + lane];
+            if (v != 0.0) mom_add(p, lane, v);
         }
     }
 }
@@ -1210,16 +1239,16 @@ __global__ void __launch_bounds__(512, 1) cgb_hard_kernel(const __grid_constant_
             if (p.speed) p.speed[loc] = v;
             if (p.trials) p.trials[loc] = nt;
             if (p.moments && nt > 0) {
-                atomicAdd(p.moments + 3, v * v);
-                atomicAdd(p.moments + 8, vx); atomicAdd(p.moments + 9, vy); atomicAdd(p.moments + 10, vz);
+                mom_add(p, 3, v * v);
+                mom_add(p, 8, vx); mom_add(p, 9, vy); mom_add(p, 10, vz);
             }
         }
         if (p.moments) {
             if (nt > 0) {
-                atomicAdd(p.moments + 1, (double)nt);
-                atomicMax((unsigned long long*)(p.moments + 2), (unsigned long long)__double_as_longlong((double)nt));
+                mom_add(p, 1, (double)nt);
+                mom_max(p, 2, (double)nt);
             } else {
-                atomicAdd(p.moments + 13, 1.0);
+                mom_add(p, 13, 1.0);
             }
         }
     }
@@ -1464,6 +1493,13 @@ static int fill_params(const cgb_sample_args* a, SampleParams& sp, const char* w
     sp.hu = a->hu;
     sp.radius_period = a->radius_period;
     CGB_REQUIRE(a->radius_period >= 0, "%s: negative radius_period", who);
+    CGB_REQUIRE(a->n_peers >= 0 && a->n_peers <= CGB_MAX_PEERS, "%s: n_peers must be 0..%d", who, CGB_MAX_PEERS);
+    sp.n_peers = a->n_peers;
+    for (int r = 0; r < a->n_peers; ++r) {
+        CGB_REQUIRE(a->d_peer_moments[r] != nullptr, "%s: null peer moment buffer %d", who, r);
+        sp.peer_moments[r] = a->d_peer_moments[r];
+    }
+    if (a->n_peers > 0) sp.moments = a->d_peer_moments[0];  // "moments requested" for the kernels
     return CGB_OK;
 }
 

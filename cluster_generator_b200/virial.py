@@ -262,6 +262,7 @@ class VirialEquilibrium:
         rng="device",
         shard=None,
         diagnostics=True,
+        peer_moments=None,
     ):
         """
         Generate a set of dark matter or star particles in virial equilibrium
@@ -280,6 +281,9 @@ class VirialEquilibrium:
             213-214), so those fields equal the reference's for the same ``prng``.
         shard : (rank, world) -- generate only this rank's contiguous index range;
             output is bit-identical to the corresponding slice of a single-GPU run.
+        peer_moments : :class:`~cluster_generator_b200.peer.PeerMoments` -- fuse the moment
+            all-reduce into the kernel (sub_sample == 1): the diagnostics hold the global
+            sums after ``peer_moments.fence()``, no NCCL call follows the kernel.
         """
         num_particles = int(num_particles)
         sub_sample = int(sub_sample)
@@ -321,6 +325,12 @@ class VirialEquilibrium:
         mass = torch.empty(n_loc, dtype=dtype, device=dev)
         pot = torch.empty(n_loc, dtype=dtype, device=dev) if compute_potential else None
         moments = torch.zeros(N.CGB_NMOMENTS, dtype=torch.float64, device=dev) if diagnostics else None
+        peer_slot = None
+        if peer_moments is not None:
+            if sub_sample != 1:
+                raise ValueError("peer_moments needs sub_sample == 1")
+            peer_slot = peer_moments.next_slot()  # taken on every rank, also by ranks with no particles
+            moments = peer_moments.slot(peer_slot)
         pmass = tabs.mtot / num_particles if num_particles > 0 else 0.0  # virial.py:225-227
 
         def base_args(begin, end, ld):
@@ -352,6 +362,8 @@ class VirialEquilibrium:
             a.d_pos, a.d_vel, a.d_mass = pos.data_ptr(), vel.data_ptr(), mass.data_ptr()
             a.d_pot = pot.data_ptr() if pot is not None else None
             a.d_moments = moments.data_ptr() if moments is not None else None
+            if peer_slot is not None:
+                peer_moments.attach(a, peer_slot)
             host_u(a, lo, hi, True)
             N.check(L.cgb_sample_particles(N.ctypes.byref(a), N.ptr(tabs.scratch), tabs.scratch.numel(),
                                            N.stream_ptr()))
@@ -393,7 +405,7 @@ class VirialEquilibrium:
             fields[key, "particle_potential"] = pot
         diag = {}
         if moments is not None:
-            diag[key] = SamplerDiagnostics(moments, shard)
+            diag[key] = SamplerDiagnostics(moments, shard, reduced=peer_slot is not None)
         del keep
         return ClusterParticles(key, fields, diag)
 
@@ -401,15 +413,19 @@ class VirialEquilibrium:
 class SamplerDiagnostics:
     """Kernel-side moments of one generation call (lazy D2H; optional all-reduce)."""
 
-    def __init__(self, moments: torch.Tensor, shard=None):
+    def __init__(self, moments: torch.Tensor, shard=None, reduced=False):
         self.moments = moments
         self.shard = shard
+        #: True when the kernels already summed over ranks (PeerMoments); all_reduce is then a no-op
+        self.reduced = reduced
 
     def all_reduce(self):
         """Sum the moments over the ranks of the default process group (NCCL on GPUs);
         the only collective of the path."""
         import torch.distributed as dist
 
+        if self.reduced:
+            return self
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             mx = self.moments[2:3].clone()
             dist.all_reduce(self.moments, op=dist.ReduceOp.SUM)

@@ -48,6 +48,8 @@ extern "C" {
                                 what InterpolatedUnivariateSpline raises at virial.py:45) */
 #define CGB_E_IO (-5)        /* file could not be created / read / parsed (IOError)      */
 
+#define CGB_MAX_PEERS 8 /* ranks of one NVSwitch domain whose moment buffers a kernel can update */
+
 #define CGB_STREAM_RADIUS 0u
 #define CGB_STREAM_POS_DIR 1u
 #define CGB_STREAM_VEL_TRIAL 2u
@@ -215,6 +217,15 @@ typedef struct cgb_sample_args {
        np.tile(radius_sub, sub_sample); directions stay per particle.  d_u_r is then the
        FULL radius_period-long array, indexed by id % radius_period. */
     int64_t radius_period;
+    /* n_peers > 0 (cgb_sample_particles / cgb_generate_velocities path): the moment all-reduce of
+       the path fused into the kernel -- instead of d_moments, the
+       kernel's final flush adds its partial sums to d_peer_moments[0..n_peers), one buffer per
+       rank (this rank's own and the peers', mapped with cgb_peer_open), with system-scope
+       atomics over NVLink.  After every rank's kernel has completed, each buffer holds the
+       global moments; no collective launch follows the kernel. */
+    int32_t n_peers;
+    int32_t pad_peers;
+    double *d_peer_moments[CGB_MAX_PEERS];
 } cgb_sample_args;
 
 /* P+R+E+V fused: replaces VirialEquilibrium.generate_particles (virial.py:108-236)
@@ -350,6 +361,17 @@ int cgb_h5_attr_name(cgb_h5_file *f, const char *obj_path, int i, char *buf, int
 int cgb_h5_attr_info(cgb_h5_file *f, const char *obj_path, const char *name, int *dtype,
                      int64_t *count, size_t *bytes);
 int cgb_h5_read_attr(cgb_h5_file *f, const char *obj_path, const char *name, void *out, size_t bytes);
+
+/* ------------------------------------------------------------------------ */
+/* Peer-visible device buffers for the fused moment all-reduce (one process per GPU):
+ * cgb_peer_alloc: zero-filled device allocation + its 64-byte CUDA IPC handle, which the caller
+ * sends to the other ranks (any transport; torch.distributed in the host mirror);
+ * cgb_peer_open maps another rank's allocation into this process (peer access over NVLink is
+ * enabled as needed); cgb_peer_close / cgb_peer_free undo them. */
+int cgb_peer_alloc(size_t bytes, void **d_ptr, unsigned char handle_out[64]);
+int cgb_peer_open(const unsigned char handle[64], void **d_ptr);
+int cgb_peer_close(void *d_ptr);
+int cgb_peer_free(void *d_ptr);
 
 #ifdef __cplusplus
 }

@@ -42,6 +42,7 @@ def test_ctypes_structs_match_the_c_header_layout():
              offsetof(cgb_sampler_desc, d_aux_t), offsetof(cgb_sampler_desc, d_aux_c));
       printf("%zu %zu %zu %zu %zu\n", offsetof(cgb_sample_args, seed), offsetof(cgb_sample_args, d_pos),
              offsetof(cgb_sample_args, ld), offsetof(cgb_sample_args, d_moments), offsetof(cgb_sample_args, hu));
+      printf("%zu %zu\n", offsetof(cgb_sample_args, n_peers), offsetof(cgb_sample_args, d_peer_moments));
       return 0; }'''
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "probe.c")
@@ -53,7 +54,8 @@ def test_ctypes_structs_match_the_c_header_layout():
     D, H, A = N.SamplerDesc, N.HostUniforms, N.SampleArgs
     want = [ctypes.sizeof(D), ctypes.sizeof(H), ctypes.sizeof(A),
             D.d_psi_t.offset, D.n_f.offset, D.d_aux_t.offset, D.d_aux_c.offset,
-            A.seed.offset, A.d_pos.offset, A.ld.offset, A.d_moments.offset, A.hu.offset]
+            A.seed.offset, A.d_pos.offset, A.ld.offset, A.d_moments.offset, A.hu.offset,
+            A.n_peers.offset, A.d_peer_moments.offset]
     assert got == want
 
 

@@ -193,7 +193,7 @@ void pad8(std::vector<uint8_t>& v)
 }
 
 // datatype message body (spec IV.A.2.d)
-std::vector<uint8_t> encode_dtype(int dt, size_t strlen_fixed = 0)
+std::vector<uint8_t> encode_dtype(int dt)
 {
     std::vector<uint8_t> v;
     switch (dt) {
@@ -212,7 +212,6 @@ std::vector<uint8_t> encode_dtype(int dt, size_t strlen_fixed = 0)
         v = {0x19, 0x01, 0x01, 0x00, 16, 0, 0, 0, 0x10, 0x00, 0, 0, 1, 0, 0, 0, 0, 0, 8, 0};
         break;
     }
-    (void)strlen_fixed;
     return v;
 }
 

@@ -294,7 +294,9 @@ class ClusterParticles:
                     a = f.read(path)
                     if name != "particle_index":
                         unit = f.attrs(path).get("units", FIELD_UNITS.get(name, ""))
-                        a = a.astype(np.float64) * _to_galactic(unit)
+                        scale = _to_galactic(unit)
+                        if a.dtype != np.float64 or scale != 1.0:  # (no extra host pass otherwise)
+                            a = a.astype(np.float64) * scale
                         units[ptype, name] = _galactic_units(unit)
                     fields[ptype, name] = _to_device_planes(a, device)
         out = cls(ptypes, fields)

@@ -35,6 +35,7 @@ METRIC = "particles/sec (pos+vel, device-timed)"
 UNIT = "particles/s"
 F_FIXED, F_TRIAL = 200.0, 52.0   # algorithmic flop per DM particle = 200 + 52 * T
 B_DM, B_GAS = 56.0, 72.0         # algorithmic bytes written per particle (fp64)
+NCU_WARP_INSTR_PER_LAUNCH = 5.348e8  # smsp__inst_executed.sum of the same capture (1e7 Vikhlinin DM particles)
 NCU_DRAM_BYTES_PER_LAUNCH = 509.5e6  # 1.8 MB read + 507.7 MB written (algorithmic: 560 MB, part still in L2)
 
 
@@ -415,6 +416,9 @@ def run_cuda(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = 2.0 * n_glob / float(te[0])
 
+    if peer is not None:
+        mom = mom.copy()
+        peer.close()  # collective: unmap the peers' buffers, then free ours
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -423,6 +427,8 @@ def run_cuda(args):
     # ---- roofline of the dominant kernel (cgb_sample_kernel) ----
     dfma = N.ctypes.c_double()
     ffma = N.ctypes.c_double()
+    sms = N.ctypes.c_int()
+    N.check(L.cgb_device_sm_count(N.ctypes.byref(sms)))
     N.check(L.cgb_measure_dfma_tflops(4096, N.ctypes.byref(dfma), N.stream_ptr()))
     N.check(L.cgb_measure_ffma_tflops(4096, N.ctypes.byref(ffma), N.stream_ptr()))
     peaks = {}
@@ -451,6 +457,15 @@ def run_cuda(args):
         "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
         "exact_fp64_evaluations_per_trial": mom[15] / max(mom[1], 1.0),
+        # what actually bounds the kernel: warp-instruction issue slots (4 schedulers per SM, one
+        # warp-instruction per clock each); instruction count from the committed ncu capture,
+        # duration and clock measured live
+        "issue": {"warp_instructions": NCU_WARP_INSTR_PER_LAUNCH * n / 1.0e7,
+                  "achieved": NCU_WARP_INSTR_PER_LAUNCH * n / 1.0e7 / k_s,
+                  "peak": sms.value * 4 * (clk["sm_mhz"] or 1965.0) * 1.0e6 if clk else None,
+                  "unit": "warp-instructions/s",
+                  "frac": (NCU_WARP_INSTR_PER_LAUNCH * n / 1.0e7 / k_s) /
+                          (sms.value * 4 * (clk["sm_mhz"] or 1965.0) * 1.0e6) if clk else None},
     }
 
     # ---- CPU baseline (bounded sample, 1 core: the reference is single-threaded) ----

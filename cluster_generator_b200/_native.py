@@ -120,6 +120,7 @@ SYMBOLS = [
     ("cgb_h5_dataset_info", c_int, [c_void_p, c_char_p, POINTER(c_int), POINTER(c_int), POINTER(c_int64),
                                     POINTER(c_int64)]),
     ("cgb_h5_read_dataset", c_int, [c_void_p, c_char_p, c_void_p, c_size_t]),
+    ("cgb_h5_read_dataset_device", c_int, [c_void_p, c_char_p, c_void_p, c_int, c_int64, c_double, c_void_p]),
     ("cgb_h5_num_attrs", c_int, [c_void_p, c_char_p, POINTER(c_int)]),
     ("cgb_h5_attr_name", c_int, [c_void_p, c_char_p, c_int, c_char_p, c_int]),
     ("cgb_h5_attr_info", c_int, [c_void_p, c_char_p, c_char_p, POINTER(c_int), POINTER(c_int64), POINTER(c_size_t)]),

@@ -522,6 +522,41 @@ void launch_pack(const void* src, long long ld, long long first, long long m, in
                                                                       (DstT*)dst);
 }
 
+// interleaved (m, ncomp) rows of SrcT -> (ncomp, ld) planes of DstT, scaled (the read direction)
+template <typename SrcT, typename DstT>
+__global__ void cgb_h5_unpack_kernel(const SrcT* __restrict__ src, long long ld, long long first, long long m,
+                                     int ncomp, double scale, DstT* __restrict__ dst)
+{
+    const long long total = m * ncomp;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < total;
+         j += (long long)gridDim.x * blockDim.x) {
+        const long long i = j / ncomp;
+        const int k = (int)(j - i * ncomp);
+        dst[k * ld + first + i] = (DstT)((double)src[j] * scale);
+    }
+}
+
+template <typename SrcT, typename DstT>
+void launch_unpack(const void* src, long long ld, long long first, long long m, int ncomp, double scale, void* dst,
+                   cudaStream_t st)
+{
+    const long long total = m * ncomp;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    cgb_h5_unpack_kernel<SrcT, DstT><<<(unsigned)blocks, 256, 0, st>>>((const SrcT*)src, ld, first, m, ncomp, scale,
+                                                                        (DstT*)dst);
+}
+
+int ensure_staging(cgb_h5_file* f)
+{
+    for (int s = 0; s < 2; ++s) {
+        if (!f->pinned[s]) CGB_CUDA_CHECK(cudaMallocHost(&f->pinned[s], STAGE_BYTES));
+        if (!f->d_stage[s]) CGB_CUDA_CHECK(cudaMalloc(&f->d_stage[s], STAGE_BYTES));
+        if (!f->ev[s]) CGB_CUDA_CHECK(cudaEventCreateWithFlags(&f->ev[s], cudaEventDisableTiming));
+    }
+    return CGB_OK;
+}
+
 // ---------------------------------------------------------------------------
 // reader
 // ---------------------------------------------------------------------------
@@ -871,11 +906,7 @@ int cgb_h5_write_dataset_device(cgb_h5_file* f, const char* path, int out_dtype,
     if (n == 0) return CGB_OK;
     CGB_REQUIRE(d_src, "cgb_h5_write_dataset_device: null source");
     cudaStream_t st = (cudaStream_t)stream;
-    for (int s = 0; s < 2; ++s) {
-        if (!f->pinned[s]) CGB_CUDA_CHECK(cudaMallocHost(&f->pinned[s], STAGE_BYTES));
-        if (!f->d_stage[s]) CGB_CUDA_CHECK(cudaMalloc(&f->d_stage[s], STAGE_BYTES));
-        if (!f->ev[s]) CGB_CUDA_CHECK(cudaEventCreateWithFlags(&f->ev[s], cudaEventDisableTiming));
-    }
+    CGB_H5_CHECK(ensure_staging(f));
     const size_t row = (size_t)ncomp * dtype_size(out_dtype);
     const int64_t per_chunk = (int64_t)(STAGE_BYTES / row);
     const bool plain = ncomp == 1 && src_dtype == out_dtype && scale == 1.0;
@@ -1059,6 +1090,57 @@ int cgb_h5_read_dataset(cgb_h5_file* f, const char* path, void* host_out, size_t
     CGB_REQUIRE(host_out, "cgb_h5_read_dataset: null buffer");
     if (!n->compact.empty()) memcpy(host_out, n->compact.data(), bytes);
     else memcpy(host_out, f->map + f->base + n->data_addr, bytes);
+    return CGB_OK;
+}
+
+int cgb_h5_read_dataset_device(cgb_h5_file* f, const char* path, void* d_dst, int dst_dtype, int64_t ld,
+                               double scale, void* stream)
+{
+    CGB_REQUIRE(f && path && !f->writing, "cgb_h5_read_dataset_device: file is not open for reading");
+    Node* n = find_node(f, path);
+    CGB_REQUIRE(n && !n->is_group, "cgb_h5: no dataset '%s'", path);
+    CGB_REQUIRE(n->dtype == CGB_H5_F32 || n->dtype == CGB_H5_F64,
+                "cgb_h5_read_dataset_device: dataset '%s' is not f32/f64", path);
+    CGB_REQUIRE(dst_dtype == CGB_H5_F32 || dst_dtype == CGB_H5_F64, "cgb_h5_read_dataset_device: output must be f32/f64");
+    CGB_REQUIRE(n->rank == 1 || n->rank == 2, "cgb_h5_read_dataset_device: dataset '%s' must have rank 1 or 2", path);
+    const int64_t rows = n->dims[0];
+    const int ncomp = n->rank == 2 ? (int)n->dims[1] : 1;
+    CGB_REQUIRE(ncomp >= 1 && ncomp <= 4 && (ncomp == 1 || ld >= rows), "cgb_h5_read_dataset_device: bad shape");
+    if (rows == 0) return CGB_OK;
+    CGB_REQUIRE(d_dst, "cgb_h5_read_dataset_device: null destination");
+    const uint8_t* src = n->compact.empty() ? f->map + f->base + n->data_addr : n->compact.data();
+    cudaStream_t st = (cudaStream_t)stream;
+    CGB_H5_CHECK(ensure_staging(f));
+    const size_t row = (size_t)ncomp * dtype_size(n->dtype);
+    const int64_t per_chunk = (int64_t)(STAGE_BYTES / row);
+    const bool plain = ncomp == 1 && n->dtype == dst_dtype && scale == 1.0;
+    const int64_t nchunks = (rows + per_chunk - 1) / per_chunk;
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int slot = (int)(c & 1);
+        const int64_t first = c * per_chunk;
+        const int64_t m = rows - first < per_chunk ? rows - first : per_chunk;
+        // the slot's previous upload (chunk c - 2) must have left the pinned buffer; the host copy
+        // out of the page cache then overlaps the upload + unpack of chunk c - 1
+        if (c >= 2) CGB_CUDA_CHECK(cudaEventSynchronize(f->ev[slot]));
+        memcpy(f->pinned[slot], src + first * row, m * row);
+        if (plain) {
+            CGB_CUDA_CHECK(cudaMemcpyAsync((char*)d_dst + first * row, f->pinned[slot], m * row,
+                                           cudaMemcpyHostToDevice, st));
+        } else {
+            CGB_CUDA_CHECK(cudaMemcpyAsync(f->d_stage[slot], f->pinned[slot], m * row, cudaMemcpyHostToDevice, st));
+            if (n->dtype == CGB_H5_F64 && dst_dtype == CGB_H5_F64)
+                launch_unpack<double, double>(f->d_stage[slot], ld, first, m, ncomp, scale, d_dst, st);
+            else if (n->dtype == CGB_H5_F64)
+                launch_unpack<double, float>(f->d_stage[slot], ld, first, m, ncomp, scale, d_dst, st);
+            else if (dst_dtype == CGB_H5_F64)
+                launch_unpack<float, double>(f->d_stage[slot], ld, first, m, ncomp, scale, d_dst, st);
+            else
+                launch_unpack<float, float>(f->d_stage[slot], ld, first, m, ncomp, scale, d_dst, st);
+            CGB_CUDA_CHECK(cudaGetLastError());
+        }
+        CGB_CUDA_CHECK(cudaEventRecord(f->ev[slot], st));
+    }
+    CGB_CUDA_CHECK(cudaStreamSynchronize(st));  // the staging slots belong to the handle
     return CGB_OK;
 }
 

@@ -141,6 +141,21 @@ class H5Reader:
         N.check(N.lib().cgb_h5_read_dataset(self._h, _b(path), c_void_p(out.ctypes.data), out.nbytes))
         return out
 
+    def read_device(self, path: str, device, dtype=torch.float64, scale: float = 1.0) -> torch.Tensor:
+        """f32/f64 dataset -> CUDA tensor of ``dtype`` (values times ``scale``) without a whole-field
+        host copy; an ``(n, k)`` dataset comes back as an ``(n, k)`` view of ``(k, n)`` planes."""
+        _, shape, _ = self.info(path)
+        if len(shape) not in (1, 2):
+            raise ValueError("read_device takes datasets of rank 1 or 2")
+        n, k = shape[0], (shape[1] if len(shape) == 2 else 1)
+        device = torch.device(device)
+        out = torch.empty((k, n) if len(shape) == 2 else (n,), dtype=dtype, device=device)
+        with torch.cuda.device(device):
+            N.check(N.lib().cgb_h5_read_dataset_device(
+                self._h, _b(path), c_void_p(out.data_ptr()), 1 if dtype == torch.float32 else 2, n, float(scale),
+                c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+        return out.T if len(shape) == 2 else out
+
     def attrs(self, obj: str) -> dict:
         n = c_int()
         N.check(N.lib().cgb_h5_num_attrs(self._h, _b(obj), byref(n)))

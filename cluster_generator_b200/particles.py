@@ -291,13 +291,20 @@ class ClusterParticles:
             for ptype in ptypes:
                 for name in f.keys(f"/{ptype}"):
                     path = f"/{ptype}/{name}"
+                    if name == "particle_index":
+                        fields[ptype, name] = _to_device_planes(f.read(path), device)
+                        continue
+                    unit = f.attrs(path).get("units", FIELD_UNITS.get(name, ""))
+                    scale = _to_galactic(unit)
+                    units[ptype, name] = _galactic_units(unit)
+                    dt, shape, _ = f.info(path)
+                    if torch.device(device).type == "cuda" and dt in (np.float32, np.float64) and len(shape) in (1, 2) \
+                            and (len(shape) == 1 or shape[1] <= 4):
+                        fields[ptype, name] = f.read_device(path, device, torch.float64, scale)
+                        continue
                     a = f.read(path)
-                    if name != "particle_index":
-                        unit = f.attrs(path).get("units", FIELD_UNITS.get(name, ""))
-                        scale = _to_galactic(unit)
-                        if a.dtype != np.float64 or scale != 1.0:  # (no extra host pass otherwise)
-                            a = a.astype(np.float64) * scale
-                        units[ptype, name] = _galactic_units(unit)
+                    if a.dtype != np.float64 or scale != 1.0:  # (no extra host pass otherwise)
+                        a = a.astype(np.float64) * scale
                     fields[ptype, name] = _to_device_planes(a, device)
         out = cls(ptypes, fields)
         out.field_units.update(units)

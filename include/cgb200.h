@@ -355,6 +355,11 @@ int cgb_h5_child_name(cgb_h5_file *f, const char *group_path, int i, char *buf, 
 int cgb_h5_dataset_info(cgb_h5_file *f, const char *path, int *dtype, int *rank, int64_t *dims4,
                         int64_t *file_offset);
 int cgb_h5_read_dataset(cgb_h5_file *f, const char *path, void *host_out, size_t bytes);
+/* (n,) or (n, k) f32/f64 dataset -> (k, ld) device planes of dst_dtype, value
+ * (dst_dtype)((double)x * scale): the read direction of cgb_h5_write_dataset_device (host copy out
+ * of the page cache overlaps upload + unpack of the previous chunk).  Synchronises `stream`. */
+int cgb_h5_read_dataset_device(cgb_h5_file *f, const char *path, void *d_dst, int dst_dtype, int64_t ld,
+                               double scale, void *stream);
 int cgb_h5_num_attrs(cgb_h5_file *f, const char *obj_path, int *n);
 int cgb_h5_attr_name(cgb_h5_file *f, const char *obj_path, int i, char *buf, int buflen);
 /* dtype 0 = attribute exists but its type is outside the subset; bytes = payload size */

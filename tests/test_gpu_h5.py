@@ -65,6 +65,16 @@ def test_device_write_spans_many_staging_chunks(tmp_path):
         np.testing.assert_array_equal(r.read("/one64"), _np(one).astype(np.float64) * 0.5)
         np.testing.assert_array_equal(r.read("/rows"), _np(rows))
         assert r.info("/empty")[:2] == (np.float64, (0, 3))
+        # the read direction: chunked upload + unpack into plane-major storage
+        back = r.read_device("/pos", "cuda")
+        assert back.shape == (n, 3) and back.T.is_contiguous() and torch.equal(back, planes.T)
+        assert torch.equal(r.read_device("/pos32s", "cuda", torch.float32), (planes.T * KMS_PER_KPCMYR).float())
+        assert torch.equal(r.read_device("/pos32s", "cuda", torch.float64, 2.0),
+                           (planes.T * KMS_PER_KPCMYR).float().double() * 2.0)
+        assert torch.equal(r.read_device("/one", "cuda", torch.float32), one)
+        assert torch.equal(r.read_device("/one64", "cuda"), one.double() * 0.5)
+        assert torch.equal(r.read_device("/rows", "cuda"), rows)
+        assert r.read_device("/empty", "cuda").shape == (0, 3)
     H.load(p)
 
 

@@ -928,7 +928,26 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
         int cur_cnt = 0, cur_next = 0, oth_left = 0;
         bool oth_live = false;
         unsigned cur_id0_lo = 0, cur_id0_hi = 0;
+        // cooperative finishes are requested by setting fin_mask / fin_kind and served at ONE
+        // place (coop_finish is large; a single inlined copy keeps the kernel's code footprint down)
+        unsigned fin_mask = 0;
+        int fin_kind = 0, fin_aux = 0;  // 1: final drain, 2: recycle buffer fin_aux, 3: long runners (fin_aux of them in the older tile)
         for (;;) {
+            if (fin_kind) {
+                finish_lanes(fin_mask);
+                if (fin_kind == 1) {
+                    if (b_live[0]) pending |= 1u;
+                    if (b_live[1]) pending |= 2u;
+                    exiting = true;
+                } else if (fin_kind == 2) {
+                    oth_live = false;
+                    pending |= 1u << fin_aux;
+                } else {
+                    oth_left -= fin_aux;
+                    if (oth_live && oth_left == 0) { oth_live = false; pending |= 1u << (cur ^ 1); }
+                }
+                fin_kind = 0;
+            }
             while (pending) {
                 const int k = __ffs(pending) - 1;
                 pending &= pending - 1;
@@ -954,19 +973,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
                     // current buffer exhausted (rare path): roll to the next tile or drain
                     const unsigned act = __ballot_sync(FULL, slot >= 0);
                     if (!more_tiles) {
-                        if (act) finish_lanes(act);  // nothing left to claim anywhere: final drain
-                        if (b_live[0]) pending |= 1u;
-                        if (b_live[1]) pending |= 2u;
-                        exiting = true;
+                        fin_mask = act; fin_kind = 1;  // nothing left to claim anywhere: final drain
                         continue;
                     }
                     const int nxt = cur ^ 1;
                     if (oth_live) {
                         // recycle: the older tile's stragglers are finished by the whole warp,
                         // then it is written out at the top of the loop
-                        finish_lanes(__ballot_sync(FULL, slot >= 0 && (slot >= TILE) == (nxt == 1)));
-                        oth_live = false;
-                        pending |= 1u << nxt;
+                        fin_mask = __ballot_sync(FULL, slot >= 0 && (slot >= TILE) == (nxt == 1));
+                        fin_kind = 2; fin_aux = nxt;
                         continue;
                     }
                     if (!acquire(nxt)) continue;  // more_tiles is now false: drains next round
@@ -1099,9 +1114,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
             const unsigned lng = __ballot_sync(FULL, slot >= 0 && pair >= LANE_CAP_PAIRS);
             if (lng) {
                 const unsigned in_oth = __ballot_sync(FULL, slot >= 0 && (slot >= TILE) != (cur == 1));
-                finish_lanes(lng);
-                oth_left -= __popc(lng & in_oth);
-                if (oth_live && oth_left == 0) { oth_live = false; pending |= 1u << (cur ^ 1); }
+                fin_mask = lng; fin_kind = 3; fin_aux = __popc(lng & in_oth);
             }
         }
     }

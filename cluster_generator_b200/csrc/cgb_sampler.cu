@@ -568,6 +568,17 @@ __device__ __noinline__ PairResult resolve_pair(const Tables& T, Philox4 w, int 
     return r;
 }
 
+// outcome of a pair from its two screen results; the exact path only where it matters
+__device__ __forceinline__ PairResult decide_pair(const Tables& T, const Philox4& w, int sa, int sb,
+                                                  const double* ppsi, const double* pvesc, const double* penv)
+{
+    if (sa == 2 || (sa == 0 && sb == 2)) return resolve_pair(T, w, sa, sb, *ppsi, *pvesc, penv);
+    PairResult r;
+    r.n_exact = 0;
+    r.acc = (sa == 1) ? 1 : ((sb == 1) ? 2 : 0);
+    return r;
+}
+
 // evaluate the two trials of one Philox call for one particle
 __device__ __forceinline__ PairResult eval_pair(const Tables& T, const float2* s_screen,
                                                 const Philox4& w, float ps, float vs, float es,
@@ -576,11 +587,7 @@ __device__ __forceinline__ PairResult eval_pair(const Tables& T, const float2* s
 {
     const int sa = screen_trial(s_screen, T.inv_w_f, w.x, w.y, ps, vs, es);
     const int sb = screen_trial(s_screen, T.inv_w_f, w.z, w.w, ps, vs, es);
-    if (sa == 2 || (sa == 0 && sb == 2)) return resolve_pair(T, w, sa, sb, *ppsi, *pvesc, penv);
-    PairResult r;
-    r.n_exact = 0;
-    r.acc = (sa == 1) ? 1 : ((sb == 1) ? 2 : 0);
-    return r;
+    return decide_pair(T, w, sa, sb, ppsi, pvesc, penv);
 }
 
 template <typename OutT>
@@ -1053,24 +1060,31 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
                 } else
 #endif
                 {
-                    PairResult r = eval_pair(T, s_screen, w0, ps, vs, es, s_psi + slot, s_ves + slot, env_ptr(slot));
+#if LEAN_SCREEN_ALL
+#define CGB_PAIR(k, w, ta, tb) decide_pair(T, w, ta, tb, s_psi + slot, s_ves + slot, env_ptr(slot))
+#else
+#define CGB_PAIR(k, w, ta, tb) eval_pair(T, s_screen, w, ps, vs, es, s_psi + slot, s_ves + slot, env_ptr(slot))
+                    const int t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0, t6 = 0, t7 = 0;
+                    (void)t0; (void)t1; (void)t2; (void)t3; (void)t4; (void)t5; (void)t6; (void)t7;
+#endif
+                    PairResult r = CGB_PAIR(0, w0, t0, t1);
                     m_exact += r.n_exact;
                     wacc = (r.acc == 1) ? w0.x : w0.z;
                     ntr = 2u * pair + (unsigned)r.acc;
                     if (!r.acc) {
-                        r = eval_pair(T, s_screen, w1, ps, vs, es, s_psi + slot, s_ves + slot, env_ptr(slot));
+                        r = CGB_PAIR(1, w1, t2, t3);
                         m_exact += r.n_exact;
                         wacc = (r.acc == 1) ? w1.x : w1.z;
                         ntr = 2u * pair + 2u + (unsigned)r.acc;
 #if LEAN_PAIRS >= 3
                         if (!r.acc) {
-                            r = eval_pair(T, s_screen, w2, ps, vs, es, s_psi + slot, s_ves + slot, env_ptr(slot));
+                            r = CGB_PAIR(2, w2, t4, t5);
                             m_exact += r.n_exact;
                             wacc = (r.acc == 1) ? w2.x : w2.z;
                             ntr = 2u * pair + 4u + (unsigned)r.acc;
 #if LEAN_PAIRS >= 4
                             if (!r.acc) {
-                                r = eval_pair(T, s_screen, w3, ps, vs, es, s_psi + slot, s_ves + slot, env_ptr(slot));
+                                r = CGB_PAIR(3, w3, t6, t7);
                                 m_exact += r.n_exact;
                                 wacc = (r.acc == 1) ? w3.x : w3.z;
                                 ntr = 2u * pair + 6u + (unsigned)r.acc;
@@ -1079,6 +1093,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
                         }
 #endif
                     }
+#undef CGB_PAIR
                     acc = r.acc;
                 }
                 if (acc) {

@@ -1004,10 +1004,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
                     continue;
                 }
             }
-            // ---- one Philox call = two trials for every active lane ----
+            // ---- LEAN_PAIRS Philox calls = 2 * LEAN_PAIRS trials for every active lane ----
             bool done_oth = false;
             if (slot >= 0) {
-#if LEAN_PAIRS >= 2
+                static_assert(LEAN_PAIRS >= 2 && LEAN_PAIRS <= 4, "2..4 trial pairs per iteration");
                 // LEAN_PAIRS independent Philox chains per iteration (trial pairs pair ..
                 // pair + LEAN_PAIRS - 1): more ILP and less loop overhead per trial; the later
                 // pairs' work is discarded when an earlier one accepts
@@ -1104,20 +1104,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
                 } else {
                     pair += (unsigned)LEAN_PAIRS;
                 }
-#else
-                const Philox4 w = philox_rk(p.rk, id_lo, id_hi, pair, CGB_STREAM_VEL_TRIAL);
-                const PairResult r = eval_pair(T, s_screen, w, ps, vs, es, s_psi + slot, s_ves + slot,
-                                               env_ptr(slot));
-                m_exact += r.n_exact;
-                if (r.acc) {
-                    s_wa[slot] = (r.acc == 1) ? w.x : w.z;
-                    s_tri[slot] = (int)(2u * pair + (unsigned)r.acc);
-                    done_oth = (slot >= TILE) != (cur == 1);
-                    slot = -1;
-                } else {
-                    ++pair;
-                }
-#endif
             }
             // particles of the older tile that just finished; the tile goes out when all did
             const unsigned dn = __ballot_sync(FULL, done_oth);

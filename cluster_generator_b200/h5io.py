@@ -64,10 +64,11 @@ class H5Writer:
         else:
             raise ValueError("write_device takes (n,) or (n, k) tensors")
         ld = planes.stride(0) if k > 1 else n
-        N.check(N.lib().cgb_h5_write_dataset_device(
-            self._h, _b(path), _CODES[out_dtype], c_void_p(planes.data_ptr()),
-            1 if t.dtype == torch.float32 else 2, n, k, ld, float(scale),
-            c_void_p(torch.cuda.current_stream(t.device).cuda_stream)))
+        with torch.cuda.device(t.device):  # staging buffers and the pack kernel live on t's device
+            N.check(N.lib().cgb_h5_write_dataset_device(
+                self._h, _b(path), _CODES[out_dtype], c_void_p(planes.data_ptr()),
+                1 if t.dtype == torch.float32 else 2, n, k, ld, float(scale),
+                c_void_p(torch.cuda.current_stream(t.device).cuda_stream)))
 
     def set_attr(self, obj: str, name: str, value) -> None:
         if isinstance(value, str):

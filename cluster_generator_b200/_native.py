@@ -103,6 +103,8 @@ SYMBOLS = [
                               c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     ("cgb_resample_gas", c_int, [POINTER(HaloTables), c_int, c_void_p, c_int64, c_int64, c_int, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    ("cgb_particle_histograms", c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int64, c_int, c_double,
+                                        c_double, c_double, c_double, c_int, c_void_p, c_void_p]),
     ("cgb_peer_alloc", c_int, [c_size_t, POINTER(c_void_p), c_char_p]),
     ("cgb_peer_open", c_int, [c_char_p, POINTER(c_void_p)]),
     ("cgb_peer_close", c_int, [c_void_p]),

@@ -229,3 +229,72 @@ extern "C" int cgb_map_field(const double* d_gx, const double* d_gy, const doubl
     CGB_CUDA_CHECK(cudaGetLastError());
     return CGB_OK;
 }
+
+// ---------------------------------------------------------------------------
+// virial-check histograms: r, |v| and E = psi(r) - v^2/2 of a particle set
+// ---------------------------------------------------------------------------
+struct HistParams {
+    const double* psi;  // ppform workspace of psi(r)
+    int n_psi, nbins;
+    const void* pos; const void* vel; long long ld, n;
+    double r_lo, inv_dlog, inv_dv, inv_de;
+    unsigned long long* hist;
+};
+
+// HBM-bound (48 B read per fp64 particle); per-CTA shared-memory counters, one flush per CTA
+template <typename T>
+__global__ void __launch_bounds__(256) cgb_hist_kernel(const __grid_constant__ HistParams p)
+{
+    extern __shared__ unsigned int s_h[];  // [3][nbins]
+    const int nb = p.nbins;
+    for (int i = threadIdx.x; i < 3 * nb; i += blockDim.x) s_h[i] = 0u;
+    __syncthreads();
+    const T* pos = (const T*)p.pos;
+    const T* vel = (const T*)p.vel;
+    const int nint = p.n_psi - 3;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
+        const double x = (double)pos[i], y = (double)pos[p.ld + i], z = (double)pos[2 * p.ld + i];
+        const double vx = (double)vel[i], vy = (double)vel[p.ld + i], vz = (double)vel[2 * p.ld + i];
+        const double r = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
+        const double v2 = __dadd_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)), __dmul_rn(vz, vz));
+        const double psi = rs_eval(p.psi, p.n_psi, rs_find(p.psi, nint, r), r);
+        const double e = __dsub_rn(psi, __dmul_rn(0.5, v2));
+        // out-of-range (and NaN) values land in the end bins
+        const int br = min(max(__double2int_rd(__dmul_rn(log(r / p.r_lo), p.inv_dlog)), 0), nb - 1);
+        const int bv = min(max(__double2int_rd(__dmul_rn(sqrt(v2), p.inv_dv)), 0), nb - 1);
+        const int be = min(max(__double2int_rd(__dmul_rn(e, p.inv_de)), 0), nb - 1);
+        atomicAdd(s_h + br, 1u);
+        atomicAdd(s_h + nb + bv, 1u);
+        atomicAdd(s_h + 2 * nb + be, 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * nb; i += blockDim.x)
+        if (s_h[i]) atomicAdd(p.hist + i, (unsigned long long)s_h[i]);
+}
+
+extern "C" int cgb_particle_histograms(const double* d_psi_pp, int n_psi, const void* d_pos, const void* d_vel,
+                                       int64_t ld, int64_t n, int dtype, double r_lo, double r_hi, double v_max,
+                                       double e_max, int nbins, unsigned long long* d_hist, void* stream)
+{
+    CGB_REQUIRE(d_psi_pp && n_psi >= 4, "cgb_particle_histograms: psi spline needs >= 4 points");
+    CGB_REQUIRE(nbins >= 1 && nbins <= 4096, "cgb_particle_histograms: nbins must be 1..4096");
+    CGB_REQUIRE(r_lo > 0.0 && r_hi > r_lo && v_max > 0.0 && e_max > 0.0, "cgb_particle_histograms: bad ranges");
+    CGB_REQUIRE(n >= 0 && ld >= n && d_hist, "cgb_particle_histograms: bad shape");
+    CGB_REQUIRE(dtype == CGB_DTYPE_F64 || dtype == CGB_DTYPE_F32, "cgb_particle_histograms: dtype %d", dtype);
+    if (n == 0) return CGB_OK;
+    CGB_REQUIRE(d_pos && d_vel, "cgb_particle_histograms: null particle buffers");
+    HistParams p;
+    p.psi = d_psi_pp; p.n_psi = n_psi; p.nbins = nbins;
+    p.pos = d_pos; p.vel = d_vel; p.ld = ld; p.n = n;
+    p.r_lo = r_lo; p.inv_dlog = (double)nbins / log(r_hi / r_lo);
+    p.inv_dv = (double)nbins / v_max; p.inv_de = (double)nbins / e_max;
+    p.hist = d_hist;
+    const unsigned blocks = (unsigned)min((long long)((n + 255) / 256), 148LL * 8);
+    const size_t smem = (size_t)3 * nbins * sizeof(unsigned int);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == CGB_DTYPE_F32) cgb_hist_kernel<float><<<blocks, 256, smem, s>>>(p);
+    else cgb_hist_kernel<double><<<blocks, 256, smem, s>>>(p);
+    CGB_CUDA_CHECK(cudaGetLastError());
+    return CGB_OK;
+}

@@ -169,6 +169,7 @@ class VirialEquilibrium:
         self.ptype = ptype
         self.model = model
         self._tables = {}
+        self._psi_pp = None
         self.g = None
         self.qags_last = self.qags_ier = None
         if df is None:
@@ -233,6 +234,70 @@ class VirialEquilibrium:
             np.abs(chk).max(),
         )
         return rho, chk
+
+    # ------------------------------------------------------------------ #
+    def particle_histograms(self, particles, nbins=256, all_reduce=False):
+        """
+        Virial-check histograms of this species' particles (north_star item 4): counts of r
+        (``nbins`` log-spaced bins over the model's radial range), |v| (linear up to the largest
+        escape speed) and E = psi(r) - v^2/2 (linear up to psi_max), computed on the device
+        (``cgb_particle_histograms``).  The particles must be in halo-centric coordinates.
+        Counts are integers, so summing the histograms of index shards reproduces the unsharded
+        histogram exactly; ``all_reduce=True`` sums them over the default process group (NCCL).
+
+        Returns a dict: ``r``, ``v``, ``E`` (int64 CUDA tensors), ``r_edges``, ``v_edges``,
+        ``E_edges`` (NumPy), ``n``.
+        """
+        key = {"dark_matter": "dm", "stellar": "star"}[self.ptype]
+        pos, vel = particles[key, "particle_position"], particles[key, "particle_velocity"]
+        ppos, pvel = pos.T, vel.T
+        if not (ppos.is_contiguous() and pvel.is_contiguous()):
+            ppos, pvel = ppos.contiguous(), pvel.contiguous()
+        n = pos.shape[0]
+        if getattr(self, "_psi_pp", None) is None:
+            sp = DeviceSpline.fit(self.model["radius"].d, self.ee[::-1])
+            nb = N.lib().cgb_ppform_workspace_bytes(sp.n)
+            ws = N.workspace(nb)
+            N.check(N.lib().cgb_ppform_prepare(N.ptr(sp.t), N.ptr(sp.c), sp.n, N.ptr(ws), nb, N.stream_ptr()))
+            self._psi_pp = (ws, sp.n)
+        ws, n_psi = self._psi_pp
+        rr = self.model["radius"].d
+        r_lo, r_hi = float(rr[0]), float(rr[-1])
+        e_max = float(self.ee.max())
+        v_max = float(np.sqrt(2.0 * e_max))
+        hist = torch.zeros((3, nbins), dtype=torch.int64, device=pos.device)
+        N.check(N.lib().cgb_particle_histograms(
+            N.ptr(ws), n_psi, N.ptr(ppos), N.ptr(pvel), ppos.stride(0) if n else 0, n, _out_code(pos.dtype),
+            r_lo, r_hi, v_max, e_max, nbins, N.ptr(hist), N.stream_ptr()))
+        if all_reduce:
+            import torch.distributed as dist
+
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+                nn = torch.tensor([n], dtype=torch.int64, device=pos.device)
+                dist.all_reduce(nn, op=dist.ReduceOp.SUM)
+                n = int(nn.item())
+        return {
+            "r": hist[0], "v": hist[1], "E": hist[2], "n": n,
+            "r_edges": r_lo * np.exp(np.arange(nbins + 1) * (np.log(r_hi / r_lo) / nbins)),
+            "v_edges": np.arange(nbins + 1) * (v_max / nbins),
+            "E_edges": np.arange(nbins + 1) * (e_max / nbins),
+        }
+
+    def radial_histogram_chi2(self, hist, r_max=None):
+        """Chi-square of the radial histogram against the distribution the radius draw samples
+        exactly: P(r) is piecewise linear between the enclosed-mass table's nodes
+        (utils.py:154-166).  Returns ``(chi2, dof)`` over the bins with >= 5 expected counts."""
+        density, mass = f"{self.ptype}_density", f"{self.ptype}_mass"
+        nonzero = self.model[density].d > 0.0
+        P_r, r_cdf, _ = radius_cdf_table(self.model["radius"].d[nonzero], self.model[mass].d[nonzero], r_max)
+        cdf = np.interp(hist["r_edges"], r_cdf, P_r, left=0.0, right=1.0)
+        cdf[0], cdf[-1] = 0.0, 1.0                       # the end bins collect everything outside
+        expected = hist["n"] * np.diff(cdf)
+        obs = hist["r"].cpu().numpy().astype(np.float64)
+        ok = expected >= 5.0
+        chi2 = float((((obs - expected) ** 2)[ok] / expected[ok]).sum())
+        return chi2, int(ok.sum()) - 1
 
     # ------------------------------------------------------------------ #
     def sampler_tables(self, r_max=None) -> SamplerTables:

@@ -296,6 +296,17 @@ int cgb_resample_gas(const cgb_halo_tables *halos, int num_halos, const void *d_
                      int64_t n, int dtype, void *d_density, void *d_thermal, void *d_vel,
                      void *d_mass, int use_radii, void *stream);
 
+/* Virial-check histograms (north_star item 4): counts of r (log-spaced
+ * bins on [r_lo, r_hi)), |v| (linear on [0, v_max)) and E = psi(r) - v^2/2 (linear on
+ * [0, e_max)) of a particle set in halo-centric coordinates; out-of-range values fall into the
+ * first / last bin.  d_psi_pp: ppform (cgb_ppform_prepare) of the relative-potential spline
+ * psi(r) = IUS(radius, -Phi) (virial.py:152) with n_psi points.  d_pos / d_vel: (3, ld) planes.
+ * d_hist: uint64[3][nbins] (r, |v|, E), ACCUMULATED (caller zeroes).  Integer counts: the sum
+ * over index shards equals the unsharded histogram exactly, so ranks all-reduce them (SUM). */
+int cgb_particle_histograms(const double *d_psi_pp, int n_psi, const void *d_pos, const void *d_vel,
+                            int64_t ld, int64_t n, int dtype, double r_lo, double r_hi, double v_max,
+                            double e_max, int nbins, unsigned long long *d_hist, void *stream);
+
 /* 3-D field -> particles ("next" row 4): tri-linear interpolation of up to three gridded
  * components at the particle positions, zero outside the grid.
  *   replaces ClusterField.map_field_to_particles (fields.py:308-338), i.e.

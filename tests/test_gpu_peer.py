@@ -88,8 +88,13 @@ scale = 2.0                                  # slot 1 holds calls 1 and 5 (same 
 assert got["particles"] == scale * n and got["sum_trials"] == scale * want["sum_trials"], (got, want)
 assert got["max_trials"] == want["max_trials"]
 assert abs(got["sum_v2"] - scale * want["sum_v2"]) <= 1e-11 * got["sum_v2"]
-lo, hi = (rank * n) // world, ((rank + 1) * n) // world
 assert torch.equal(out[1].moments, peer.slot(1))
+# virial-check histograms: integer counts, summed over ranks with the process group's all_reduce
+pv = pm.dm_virial
+mine = pm.generate_dm_particles(n, prng=1, shard=(rank, world))
+h = pv.particle_histograms(mine, nbins=32, all_reduce=True)
+hs = pv.particle_histograms(single, nbins=32)
+assert h["n"] == n and all(torch.equal(h[k], hs[k]) for k in ("r", "v", "E")), (h, hs)
 peer.close()
 dist.destroy_process_group()
 print("rank", rank, "ok")

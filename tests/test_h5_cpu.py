@@ -391,3 +391,94 @@ def test_ics_budget_split_from_model_files(tmp_path):
     assert dict(a.num_particles) == dict(b.num_particles)
     assert sum(a.num_particles["dm"]) == 100_000 and a.num_particles["dm"][0] > a.num_particles["dm"][1]
     assert a.particle_files == [None, None]
+
+
+def _move_attrs_to_continuation(src, dst, obj_path):
+    """Rewrite ``obj_path``'s v1 object header the way libhdf5 lays out a header that outgrew its
+    first chunk: the attribute messages move to a continuation block at the end of the file, the
+    first chunk keeps the other messages, a continuation message (0x0010) and NIL padding."""
+    import struct
+
+    raw = bytearray(open(src, "rb").read())
+    root_hdr = struct.unpack_from("<Q", raw, 24 + 32 + 8)[0]
+
+    def header_of(path):
+        addr = root_hdr
+        for part in [p for p in path.split("/") if p]:
+            nm, _, hs = struct.unpack_from("<HII", raw, addr + 2)
+            o, stab = addr + 16, None
+            while o < addr + 16 + hs:
+                t, sz = struct.unpack_from("<HH", raw, o)
+                if t == 0x11:
+                    stab = struct.unpack_from("<QQ", raw, o + 8)
+                o += 8 + sz
+            bt, hp = stab
+            seg = struct.unpack_from("<Q", raw, hp + 24)[0]
+            used = struct.unpack_from("<H", raw, bt + 6)[0]
+            found = None
+            for k in range(used):
+                snod = struct.unpack_from("<Q", raw, bt + 24 + 16 * k + 8)[0]
+                for e in range(struct.unpack_from("<H", raw, snod + 6)[0]):
+                    noff, oaddr = struct.unpack_from("<QQ", raw, snod + 8 + 40 * e)
+                    name = bytes(raw[seg + noff:raw.index(b"\0", seg + noff)]).decode()
+                    if name == part:
+                        found = oaddr
+            addr = found
+        return addr
+
+    addr = header_of(obj_path)
+    nm, _, hs = struct.unpack_from("<HII", raw, addr + 2)
+    keep, moved, o = [], [], addr + 16
+    while o < addr + 16 + hs:
+        t, sz = struct.unpack_from("<HH", raw, o)
+        (moved if t == 0x0C else keep).append(bytes(raw[o:o + 8 + sz]))
+        o += 8 + sz
+    assert moved, "object has no attributes"
+    cont = b"".join(moved)
+    cont_addr = (len(raw) + 7) // 8 * 8
+    first = b"".join(keep) + struct.pack("<HHBxxxQQ", 0x10, 16, 0, cont_addr, len(cont))
+    room = hs - len(first)
+    assert room >= 0 and room % 8 == 0
+    n_nil = 0
+    while room > 0:                                   # NIL messages fill what is left
+        body = min(room - 8, 65528)
+        first += struct.pack("<HHBxxx", 0, body, 0) + b"\0" * body
+        room -= 8 + body
+        n_nil += 1
+    raw[addr + 16:addr + 16 + hs] = first
+    struct.pack_into("<H", raw, addr + 2, len(keep) + 1 + n_nil + len(moved))
+    raw += b"\0" * (cont_addr - len(raw)) + cont
+    struct.pack_into("<Q", raw, 24 + 16, len(raw))    # end-of-file address
+    open(dst, "wb").write(raw)
+
+
+def test_reader_follows_object_header_continuation_blocks(tmp_path):
+    """Headers that h5py grows after creation (e.g. a Gadget ``Header`` group whose attributes are
+    added one by one) spill into continuation blocks; both readers must follow them."""
+    p = str(tmp_path / "ic.h5")
+    P = _host_particles(50)
+    P.write_to_gadget_file(p, 2000.0)
+    q = str(tmp_path / "ic_cont.h5")
+    _move_attrs_to_continuation(p, q, "/Header")
+    a, b = H.load(p), H.load(q)
+    assert list(b["children"]["Header"]["attrs"]) == list(a["children"]["Header"]["attrs"])
+    with H5Reader(p) as r0, H5Reader(q) as r1:
+        h0, h1 = r0.attrs("/Header"), r1.attrs("/Header")
+        assert list(h0) == list(h1) and len(h1) == 18
+        for k in h0:
+            np.testing.assert_array_equal(h0[k], h1[k])
+        np.testing.assert_array_equal(r0.read("/PartType1/Masses"), r1.read("/PartType1/Masses"))
+    G = ClusterParticles.from_gadget_file(q, device="cpu")
+    assert G.num_particles["gas"] == 50
+
+
+def test_unit_tables():
+    from cluster_generator_b200.particles import _to_galactic, gadget_unit_scale
+
+    assert gadget_unit_scale("Velocities", "kpc/Myr") == KMS_PER_KPCMYR
+    assert gadget_unit_scale("Masses", "Msun") == 1e-10 and gadget_unit_scale("Coordinates", "kpc") == 1.0
+    assert gadget_unit_scale("InternalEnergy", "kpc**2/Myr**2") == KMS_PER_KPCMYR**2
+    assert _to_galactic("km/s") * KMS_PER_KPCMYR == pytest.approx(1.0, rel=1e-15)
+    assert KMS_PER_KPCMYR == pytest.approx(977.79222, rel=1e-7)
+    with pytest.raises(ValueError, match="not one this package can convert"):
+        _to_galactic("furlong/fortnight")

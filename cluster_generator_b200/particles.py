@@ -156,6 +156,43 @@ class ClusterParticles:
         diag.update(other.diagnostics)
         return ClusterParticles(particle_types, fields, diag)
 
+    @classmethod
+    def from_fields(cls, fields):
+        """particles.py:227-233: particle types in order of first appearance in the keys."""
+        particle_types = []
+        for key in fields:
+            if key[0] not in particle_types:
+                particle_types.append(key[0])
+        return cls(particle_types, fields)
+
+    def set_field(self, ptype, name, value, units=None, add=False, passive_scalar=False):
+        """Add or update a particle field (particles.py:368-421).  ``value``: tensor / array with
+        one entry per particle of ``ptype``; ``units``: the units the values are in (recorded in
+        ``field_units``; the reference converts through unyt)."""
+        from .utils import mylog
+
+        ref = self.fields[ptype, "particle_mass"]
+        value = torch.as_tensor(value, device=ref.device)
+        num_particles = self.num_particles[ptype]
+        if value.shape[0] != num_particles:
+            raise ValueError(f"The length of the array needs to be {num_particles} particles!")
+        exists = (ptype, name) in self.fields
+        if exists:
+            if add:
+                self.fields[ptype, name] += value
+            else:
+                mylog.warning("Overwriting field (%s, %s).", ptype, name)
+                self.fields[ptype, name] = value
+        else:
+            if add:
+                raise RuntimeError(f"Field ({ptype}, {name}) does not exist and add=True!")
+            self.fields[ptype, name] = value
+            if passive_scalar and ptype == "gas":
+                self.passive_scalars.append(name)
+        if units is not None or not exists:
+            self.field_units[ptype, name] = units if units is not None else FIELD_UNITS.get(name, "")
+        self._update_field_names()
+
     def add_offsets(self, r_ctr, v_ctr, ptypes=None):
         """particles.py:423-451"""
         if ptypes is None:

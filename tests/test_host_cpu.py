@@ -309,3 +309,24 @@ def test_cluster_ics_particle_budget_split():
         cg.ClusterICs("m", 1, ["absent_model.h5"], [0, 0, 0], [0, 0, 0])
     with pytest.raises(ValueError):
         cg.ClusterICs("m", 2, [big], [[0, 0, 0]] * 2, [[0, 0, 0]] * 2)
+
+
+def test_set_field_and_from_fields():
+    """particles.py:227-233, 368-421 on CPU tensors."""
+    from cluster_generator_b200 import ClusterParticles
+
+    f = {("gas", "particle_mass"): torch.ones(5, dtype=torch.float64),
+         ("dm", "particle_mass"): torch.ones(3, dtype=torch.float64)}
+    p = ClusterParticles.from_fields(f)
+    assert p.particle_types == ["gas", "dm"] and p.num_particles == {"gas": 5, "dm": 3}
+    p.set_field("gas", "metallicity", np.full(5, 0.3), passive_scalar=True)
+    assert p.passive_scalars == ["metallicity"] and p.num_passive_scalars == 1
+    assert "metallicity" in p.field_names["gas"] and p.field_units["gas", "metallicity"] == ""
+    p.set_field("gas", "metallicity", torch.full((5,), 0.2, dtype=torch.float64), add=True)
+    assert torch.allclose(p["gas", "metallicity"], torch.full((5,), 0.5, dtype=torch.float64))
+    p.set_field("dm", "particle_mass", torch.full((3,), 2.0, dtype=torch.float64), units="Msun")
+    assert float(p["dm", "particle_mass"][0]) == 2.0
+    with pytest.raises(ValueError, match="needs to be 3 particles"):
+        p.set_field("dm", "x", np.zeros(4))
+    with pytest.raises(RuntimeError, match="add=True"):
+        p.set_field("dm", "x", np.zeros(3), add=True)

@@ -131,6 +131,55 @@ class ClusterModel:
             model._star_virial = VirialEquilibrium(model, ptype="stellar", df=df["star_df"][mask])
         return model
 
+    def write_model_to_binary(self, output_filename, fields_to_write=None, in_cgs=False, r_min=None,
+                              r_max=None, overwrite=False):
+        """Fortran unformatted file: one record with the number of radii, one with the
+        (num_radii, num_fields) table (model.py:399-456)."""
+        import os
+
+        from scipy.io import FortranFile
+
+        if in_cgs:
+            raise NotImplementedError("only galactic units (kpc, Msun, Myr) are written; cgs output needs unyt")
+        if fields_to_write is None:
+            fields_to_write = list(self.fields.keys())
+        if os.path.exists(output_filename) and not overwrite:
+            raise IOError(f"Cannot create {output_filename}. It exists and overwrite=False.")
+        r_min = 0.0 if r_min is None else r_min
+        r_max = self.fields["radius"].d[-1] * 2 if r_max is None else r_max
+        mask = np.logical_and(self.fields["radius"].d >= r_min, self.fields["radius"].d <= r_max)
+        with FortranFile(str(output_filename), "w") as f:
+            f.write_record(self.fields["radius"].d[mask].size)
+            f.write_record(np.array([self.fields[k].d[mask] for k in fields_to_write]).T)
+        return output_filename
+
+    def write_model_to_ascii(self, output_filename, in_cgs=False, overwrite=False):
+        """Plain-text table, one column per field, units in the header (model.py:307-340 writes an
+        astropy QTable; astropy is not available, the column layout is the same)."""
+        import os
+
+        if in_cgs:
+            raise NotImplementedError("only galactic units (kpc, Msun, Myr) are written; cgs output needs unyt")
+        if os.path.exists(output_filename) and not overwrite:
+            raise IOError(f"Cannot create {output_filename}. It exists and overwrite=False.")
+        names = list(self.fields.keys())
+        header = "unit_system=galactic\n" + " ".join(names) + "\n" + \
+                 " ".join(self.fields[k].units or "dimensionless" for k in names)
+        np.savetxt(str(output_filename), np.array([self.fields[k].d for k in names]).T, header=header)
+        return output_filename
+
+    def mass_in_radius(self, radius):
+        """Mass of each matter type inside ``radius`` (model.py:1088-1107)."""
+        r = self.fields["radius"].d
+        return {mtype: unit_array(self.fields[f"{mtype}_mass"].d[r < radius][-1], "Msun")
+                for mtype in ("total", "gas", "dark_matter", "stellar") if f"{mtype}_mass" in self.fields}
+
+    def find_radius_for_density(self, density):
+        """Radius at which the gas density falls to ``density`` [Msun/kpc**3] (model.py:1109-1113)."""
+        r = self.fields["radius"].d[::-1]
+        d = self.fields["density"].d[::-1]
+        return unit_array(np.interp(float(density), d, r), "kpc")
+
     # -- construction --------------------------------------------------------
     @classmethod
     def from_arrays(cls, fields):

@@ -330,3 +330,33 @@ def test_set_field_and_from_fields():
         p.set_field("dm", "x", np.zeros(4))
     with pytest.raises(RuntimeError, match="add=True"):
         p.set_field("dm", "x", np.zeros(3), add=True)
+
+
+def test_model_helpers_and_flat_files(tmp_path):
+    """model.py:307-340, 399-456, 1088-1113"""
+    from scipy.io import FortranFile
+
+    from tests.configs import product_model
+
+    pm = product_model("vikhlinin")
+    m = pm.mass_in_radius(1000.0)
+    r = pm["radius"].d
+    assert set(m) == {"total", "gas", "dark_matter"} and float(m["total"]) == pm["total_mass"].d[r < 1000.0][-1]
+    assert m["gas"].units == "Msun" and float(m["gas"]) < float(m["total"])
+    rho = pm["density"].d[400]
+    assert float(pm.find_radius_for_density(rho)) == pytest.approx(r[400], rel=1e-12)
+    fn = pm.write_model_to_binary(tmp_path / "m.bin", fields_to_write=["radius", "density"], r_max=500.0)
+    with FortranFile(str(fn), "r") as f:
+        n = int(f.read_ints()[0])
+        tab = f.read_reals().reshape(n, 2)
+    assert n == int((r <= 500.0).sum())
+    np.testing.assert_array_equal(tab[:, 0], r[:n])
+    np.testing.assert_array_equal(tab[:, 1], pm["density"].d[:n])
+    with pytest.raises(IOError, match="overwrite=False"):
+        pm.write_model_to_binary(tmp_path / "m.bin")
+    fa = pm.write_model_to_ascii(tmp_path / "m.txt")
+    back = np.loadtxt(str(fa))
+    assert back.shape == (pm.num_elements, len(list(pm.keys())))
+    np.testing.assert_allclose(back[:, list(pm.keys()).index("radius")], r, rtol=1e-15)
+    head = open(fa).read().splitlines()[:3]
+    assert head[0] == "# unit_system=galactic" and "radius" in head[1] and "kpc" in head[2]

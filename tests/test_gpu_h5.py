@@ -142,3 +142,9 @@ def test_ics_particle_files(tmp_path):
     third = ics2.setup_particle_ics()
     for k in first.fields:
         assert torch.equal(first[k], third[k]), k
+    # ics.py:377-422: the relaxed-particle path re-samples the same fields from the same profiles
+    dens0 = first["gas", "density"].clone()
+    again2 = ics.resample_particle_ics(first)
+    assert torch.isfinite(again2["gas", "thermal_energy"]).all()
+    inside = ((first["gas", "particle_position"] - torch.as_tensor(c1, device="cuda")).norm(dim=1) < 5000.0)
+    torch.testing.assert_close(again2["gas", "density"][inside], dens0[inside], rtol=1e-12, atol=0.0)

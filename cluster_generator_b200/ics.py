@@ -153,3 +153,51 @@ class ClusterICs:
         if self.num_halos == 2:
             return resample_two_clusters(parts, m[0], m[1], c[0], c[1], v[0], v[1], self.r_max)
         return resample_three_clusters(parts, m[0], m[1], m[2], c[0], c[1], c[2], v[0], v[1], v[2], self.r_max)
+
+    # -- parameter files (ics.py:202-320; same keys, written with PyYAML instead of ruamel) -----
+    def to_file(self, filename, overwrite=False):
+        """Write the initial-conditions description to a YAML file.  Profiles must be model
+        files (``ClusterModel.write_model_to_h5``), as in the reference."""
+        import os
+
+        import yaml
+
+        if os.path.exists(filename) and not overwrite:
+            raise RuntimeError(f"{filename} exists and overwrite=False!")
+        if not all(isinstance(p, (str, os.PathLike)) for p in self.profiles):
+            raise ValueError("to_file needs the profiles as model file names (write_model_to_h5)")
+        out = {"basename": self.basename, "num_halos": self.num_halos}
+        for i in range(self.num_halos):
+            out[f"profile{i + 1}"] = os.fspath(self.profiles[i])
+            out[f"center{i + 1}"] = [float(x) for x in self.center[i]]
+            out[f"velocity{i + 1}"] = [float(x) for x in self.velocity[i]]
+            if self.particle_files[i] is not None:
+                out[f"particle_file{i + 1}"] = os.fspath(self.particle_files[i])
+        for key in ("dm", "gas", "star", "tracer"):
+            if self.tot_np.get(key, 0) > 0:
+                out[f"num_{key}_particles"] = int(self.tot_np[key])
+        if self.mag_file is not None:
+            out["mag_file"] = self.mag_file
+        out["r_max"] = [float(x) for x in self.r_max]
+        if self.tot_np.get("tracer", 0) > 0:
+            out["r_max_tracer"] = [float(x) for x in self.r_max_tracer]
+        with open(filename, "w") as f:
+            yaml.safe_dump(out, f, sort_keys=False)
+        return filename
+
+    @classmethod
+    def from_file(cls, filename):
+        """Read a YAML file written by :meth:`to_file` (or by the reference)."""
+        import yaml
+
+        with open(filename, "r") as f:
+            params = yaml.safe_load(f)
+        num_halos = params["num_halos"]
+        rng = range(1, num_halos + 1)
+        num_particles = {k: params.get(f"num_{k}_particles", 0) for k in ("gas", "dm", "star", "tracer")}
+        r_max = params.get("r_max", 20000.0)
+        return cls(params["basename"], num_halos, [params[f"profile{i}"] for i in rng],
+                   [np.array(params[f"center{i}"]) for i in rng], [np.array(params[f"velocity{i}"]) for i in rng],
+                   num_particles=num_particles, mag_file=params.get("mag_file", None),
+                   particle_files=[params.get(f"particle_file{i}", None) for i in rng],
+                   r_max=r_max, r_max_tracer=params.get("r_max_tracer", r_max))

@@ -482,3 +482,30 @@ def test_unit_tables():
     assert KMS_PER_KPCMYR == pytest.approx(977.79222, rel=1e-7)
     with pytest.raises(ValueError, match="not one this package can convert"):
         _to_galactic("furlong/fortnight")
+
+
+def test_ics_parameter_file_round_trip(tmp_path):
+    """ics.py:202-320: YAML keys basename / num_halos / profileN / centerN / velocityN / num_*_particles / r_max."""
+    import yaml
+
+    from tests.configs import product_model
+
+    pm = product_model("vikhlinin")
+    mf = pm.write_model_to_h5(tmp_path / "halo.h5")
+    a = cg.ClusterICs("bin", 2, [mf, mf], [[0.0, 1.0, 2.0], [3.0, 4.0, 5.0]], [[0.5, 0, 0], [-0.5, 0, 0]],
+                      num_particles={"dm": 1000, "gas": 500}, r_max=[5000.0, 2000.0],
+                      particle_files=[None, "halo2_particles.h5"])
+    fn = a.to_file(tmp_path / "ics.yml")
+    raw = yaml.safe_load(open(fn))
+    assert list(raw)[:5] == ["basename", "num_halos", "profile1", "center1", "velocity1"]
+    assert raw["particle_file2"] == "halo2_particles.h5" and "particle_file1" not in raw
+    assert raw["num_dm_particles"] == 1000 and raw["r_max"] == [5000.0, 2000.0]
+    b = cg.ClusterICs.from_file(fn)
+    assert b.basename == "bin" and b.num_halos == 2 and b.profiles == [str(mf), str(mf)]
+    np.testing.assert_array_equal(b.center, a.center)
+    np.testing.assert_array_equal(b.velocity, a.velocity)
+    assert dict(b.num_particles) == dict(a.num_particles) and b.particle_files == a.particle_files
+    with pytest.raises(RuntimeError, match="overwrite=False"):
+        a.to_file(fn)
+    with pytest.raises(ValueError, match="model file names"):
+        cg.ClusterICs("x", 1, [pm], [0, 0, 0], [0, 0, 0]).to_file(tmp_path / "x.yml")

@@ -482,7 +482,9 @@ def run_cuda(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "dm_per_gpu": n, "gas_per_gpu": n, "num_points": pm.num_elements,
                    "rng": "Philox4x32-10 device", "l2": "outputs 1.28 GB/step/GPU exceed the 126 MB L2",
-                   "parallelism": f"index-sharded x{world}"},
+                   "parallelism": f"index-sharded x{world}",
+                   "moments_reduce": {"peer": "fused into the sampler kernel over peer-mapped buffers (NVLink)",
+                                      "nccl": "NCCL all_reduce per step", "local": "single GPU"}[mom_mode]},
         "fE_build_ms": min(fe_ms), "fE_build_note": "bit-equal to scipy (FITPACK-exact spline fits)",
         "fE_build_fast_ms": min(fe_fast_ms), "fE_build_fast_note": "PCR spline fits, f within 1e-11 of scipy",
         "fE_build_cpu_ms": 1e3 * fe_cpu_s, "check_virial_ms": min(cv_ms),

@@ -237,7 +237,6 @@ def run_cuda(args):
 
     import cluster_generator_b200 as cg
     from cluster_generator_b200 import _native as N
-    from cluster_generator_b200.virial import SamplerTables
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

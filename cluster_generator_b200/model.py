@@ -24,7 +24,7 @@ from scipy.interpolate import InterpolatedUnivariateSpline
 from . import _native as N
 from .particles import ClusterParticles
 from .utils import G, integrate, integrate_mass, keV, mp, mu, mue, mylog, parse_prng, seed_from_prng, unit_array
-from .virial import (PRIVATE_TRIAL_SEED, DeviceSpline, SamplerDiagnostics, SamplerTables,
+from .virial import (PRIVATE_TRIAL_SEED, DeviceSpline, SamplerDiagnostics, SamplerTables,  # noqa: F401
                      VirialEquilibrium, _out_code, radius_cdf_table, shard_bounds)
 
 _UNITS = {

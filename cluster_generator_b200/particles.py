@@ -371,12 +371,20 @@ class ClusterParticles:
         out.field_units.update(units)
         return out
 
-    def write_to_gadget_file(self, ic_filename, box_size, dtype="float32", overwrite=False, code=None):
+    def write_to_gadget_file(self, ic_filename, box_size, dtype="float32", overwrite=False, code=None, *,
+                             shard=None, shard_counts=None):
         """Write Gadget-HDF5 initial conditions (particles.py:453-552): ``PartType{0,1,2,4,5}``
         groups with Coordinates [kpc], Velocities [km/s], Masses [1e10 Msun], Density,
         InternalEnergy / Potential [km**2/s**2], sequential uint32 ParticleIDs, particles
         outside ``[0, box_size]^3`` dropped, and the ``Header`` attributes Gadget-family
-        codes read.  ``code="arepo"`` adds the ``Config`` group."""
+        codes read.  ``code="arepo"`` adds the ``Config`` group.
+
+        ``shard=(rank, world)`` (one process per GPU): this object holds rank's index shard and
+        the ranks write one file each, ``<stem>.<rank><suffix>`` -- Gadget's multi-file layout
+        (``NumFilesPerSnapshot = world``, ``NumPart_Total`` over all files, particle ids continuing
+        from file to file in the order a single-file write would give them).  The per-rank counts
+        after clipping come from one ``all_gather`` over the default process group, or from
+        ``shard_counts`` (list over ranks of ``{ptype: count}``)."""
         import os
 
         import numpy as np
@@ -384,20 +392,41 @@ class ClusterParticles:
         from .h5io import H5Writer
 
         ic_filename = str(ic_filename)
+        rank, world = (0, 1) if shard is None else shard
+        if shard is not None:
+            if not 0 <= rank < world:
+                raise ValueError(f"bad shard {shard}")
+            stem, ext = os.path.splitext(ic_filename)
+            ic_filename = f"{stem}.{rank}{ext}"
         if os.path.exists(ic_filename) and not overwrite:
             raise IOError(f"Cannot create {ic_filename}. It exists and overwrite=False.")
         if np.dtype(dtype) not in (np.dtype("float32"), np.dtype("float64")):
             raise ValueError("dtype must be 'float32' or 'float64'")
-        num_particles = {}
-        npart = 0
+        masks = {ptype: self._clip_to_box(ptype, box_size) for ptype in self.particle_types}
+        num_particles = {ptype: int(m.sum().item()) for ptype, m in masks.items()}
+        # counts[r][ptype] for every rank r
+        if shard is None:
+            counts = [num_particles]
+        elif shard_counts is not None:
+            counts = [dict(c) for c in shard_counts]
+            if len(counts) != world or any(counts[rank].get(t, 0) != n for t, n in num_particles.items()):
+                raise ValueError("shard_counts must list every rank's counts, this rank's included")
+        else:
+            import torch.distributed as dist
+
+            mine = [num_particles.get(ptype_map[g], 0) for g in ptype_map]
+            gathered = [None] * world
+            dist.all_gather_object(gathered, mine)
+            counts = [dict(zip(ptype_map.values(), g)) for g in gathered]
+        totals = {t: sum(c.get(t, 0) for c in counts) for t in ptype_map.values()}
         mass_table = np.zeros(6)
+        npart = 0  # ids already taken by the particle types written before
         with H5Writer(ic_filename, overwrite=True) as f:
             for ptype in self.particle_types:
                 gptype = rptype_map[ptype]
-                idxs = self._clip_to_box(ptype, box_size)
-                n_in = int(idxs.sum().item())
+                idxs = masks[ptype]
+                n_in = num_particles[ptype]
                 keep_all = n_in == idxs.numel()
-                num_particles[ptype] = n_in
                 f.create_group(f"/{gptype}")
                 for field in gadget_fields[ptype] + code_fields.get(code, {}).get(ptype, []):
                     if field == "ParticleIDs":
@@ -421,17 +450,19 @@ class ClusterParticles:
                     if field == "Masses" and ptype in ("star", "dm", "black_hole") and n_in:
                         m0 = np.asarray(float(fd[0].item()) * scale).astype(dtype)
                         mass_table[int(gptype[-1])] = m0
-                ids = np.arange(n_in, dtype=np.int64) + 1 + npart
+                before = sum(c.get(ptype, 0) for c in counts[:rank])
+                ids = np.arange(n_in, dtype=np.int64) + 1 + npart + before
                 f.write(f"/{gptype}/ParticleIDs", ids.astype("uint32"))
-                npart += n_in
+                npart += totals[ptype]
             f.create_group("/Header")
-            nums = np.array([num_particles.get("gas", 0), num_particles.get("dm", 0),
-                             num_particles.get("tracer", 0), 0, num_particles.get("star", 0),
-                             num_particles.get("black_hole", 0)], dtype="uint32")
+            order = ("gas", "dm", "tracer", None, "star", "black_hole")
+            nums = np.array([num_particles.get(t, 0) if t else 0 for t in order], dtype="uint32")
+            tot = np.array([totals.get(t, 0) if t else 0 for t in order], dtype=np.int64)
             header = [("Time", 0.0), ("Redshift", 0.0), ("BoxSize", float(box_size)), ("Omega0", 0.0),
                       ("OmegaLambda", 0.0), ("HubbleParam", 1.0), ("NumPart_ThisFile", nums),
-                      ("NumPart_Total", nums), ("NumPart_Total_HighWord", np.zeros(6, dtype="uint32")),
-                      ("NumFilesPerSnapshot", 1), ("MassTable", mass_table), ("Flag_Sfr", 0),
+                      ("NumPart_Total", (tot & 0xFFFFFFFF).astype("uint32")),
+                      ("NumPart_Total_HighWord", (tot >> 32).astype("uint32")),
+                      ("NumFilesPerSnapshot", world), ("MassTable", mass_table), ("Flag_Sfr", 0),
                       ("Flag_Cooling", 0), ("Flag_StellarAge", 0), ("Flag_Metals", 0), ("Flag_Feedback", 0),
                       ("Flag_DoublePrecision", 0), ("Flag_IC_Info", 0)]
             for k, v in header:

@@ -95,6 +95,20 @@ mine = pm.generate_dm_particles(n, prng=1, shard=(rank, world))
 h = pv.particle_histograms(mine, nbins=32, all_reduce=True)
 hs = pv.particle_histograms(single, nbins=32)
 assert h["n"] == n and all(torch.equal(h[k], hs[k]) for k in ("r", "v", "E")), (h, hs)
+# one Gadget file per rank (counts exchanged with all_gather_object)
+from cluster_generator_b200.h5io import H5Reader
+mine.add_offsets([1.0e4] * 3, [0.0] * 3)
+mine.write_to_gadget_file(os.path.join(sys.argv[2], "ic.h5"), 2.0e4, overwrite=True, shard=(rank, world))
+dist.barrier()
+seen, ids = 0, []
+for r in range(world):
+    with H5Reader(os.path.join(sys.argv[2], f"ic.{r}.h5")) as rd:
+        hd = rd.attrs("/Header")
+        assert hd["NumFilesPerSnapshot"] == world
+        seen += int(hd["NumPart_ThisFile"][1])
+        ids.append(rd.read("/PartType1/ParticleIDs"))
+assert seen == int(hd["NumPart_Total"][1]) <= n
+assert np.array_equal(np.concatenate(ids), np.arange(1, seen + 1, dtype=np.uint32))
 peer.close()
 dist.destroy_process_group()
 print("rank", rank, "ok")
@@ -107,7 +121,7 @@ def test_peer_moments_across_two_processes(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(_WORKER)
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", WORLD_SIZE="2")
-    procs = [subprocess.Popen([sys.executable, str(script), ROOT], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(tmp_path)], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, cwd=ROOT) for r in range(2)]
     outs = []
     for p in procs:

@@ -509,3 +509,39 @@ def test_ics_parameter_file_round_trip(tmp_path):
         a.to_file(fn)
     with pytest.raises(ValueError, match="model file names"):
         cg.ClusterICs("x", 1, [pm], [0, 0, 0], [0, 0, 0]).to_file(tmp_path / "x.yml")
+
+
+def test_gadget_multi_file_layout(tmp_path):
+    """One file per rank of an index-sharded run: same particles, ids and totals as the single file."""
+    P = _host_particles(600, seed=4)
+    box = 1000.0
+    single = H.load(P.write_to_gadget_file(tmp_path / "one.h5", box))
+    cut = {"dm": 250, "gas": 100}
+
+    def shard(lo_hi):
+        f = OrderedDict()
+        for (ptype, name), v in P.fields.items():
+            lo, hi = lo_hi[ptype]
+            f[ptype, name] = _planes(v[lo:hi].numpy()) if v.dim() == 2 else v[lo:hi].clone()
+        return ClusterParticles(["dm", "gas"], f)
+
+    parts = [shard({k: (0, c) for k, c in cut.items()}), shard({k: (c, 600) for k, c in cut.items()})]
+    counts = [{t: int(p._clip_to_box(t, box).sum()) for t in ("dm", "gas")} for p in parts]
+    files = [p.write_to_gadget_file(tmp_path / "multi.h5", box, shard=(r, 2), shard_counts=counts)
+             for r, p in enumerate(parts)]
+    assert [os.path.basename(f) for f in files] == ["multi.0.h5", "multi.1.h5"]
+    roots = [H.load(f) for f in files]
+    hs, h0, h1 = (r["children"]["Header"]["attrs"] for r in [single] + roots)
+    assert h0["NumFilesPerSnapshot"] == 2 and hs["NumFilesPerSnapshot"] == 1
+    np.testing.assert_array_equal(h0["NumPart_Total"], hs["NumPart_Total"])
+    np.testing.assert_array_equal(h0["NumPart_ThisFile"].astype(np.int64) + h1["NumPart_ThisFile"], hs["NumPart_Total"])
+    np.testing.assert_array_equal(h1["NumPart_Total_HighWord"], np.zeros(6, dtype=np.uint32))
+    np.testing.assert_array_equal(h0["MassTable"], hs["MassTable"])
+    for g in ("PartType0", "PartType1"):
+        for name, ds in single["children"][g]["children"].items():
+            both = np.concatenate([r["children"][g]["children"][name]["data"] for r in roots])
+            np.testing.assert_array_equal(both, ds["data"])       # ids included: they continue across files
+    with pytest.raises(ValueError, match="shard_counts"):
+        parts[0].write_to_gadget_file(tmp_path / "bad.h5", box, shard=(0, 2), shard_counts=counts[:1])
+    G = ClusterParticles.from_gadget_file(files[1], device="cpu")
+    assert G.num_particles == {"gas": counts[1]["gas"], "dm": counts[1]["dm"]}

@@ -477,14 +477,30 @@ class ClusterParticles:
         return len(self.passive_scalars)
 
     @classmethod
-    def from_gadget_file(cls, filename, ptypes=None, device=None):
+    def from_gadget_file(cls, filename, ptypes=None, device=None, all_files=False):
         """Read a Gadget-HDF5 snapshot / IC file into galactic units (particles.py:280-335);
-        a missing ``Masses`` dataset is filled from ``Header.MassTable``."""
+        a missing ``Masses`` dataset is filled from ``Header.MassTable``.  ``all_files=True``:
+        ``filename`` is one file ``<stem>.<i><suffix>`` of a multi-file snapshot; all
+        ``NumFilesPerSnapshot`` files are read and concatenated in file order."""
         import numpy as np
 
         from .h5io import H5Reader
 
         device = device or ("cuda" if torch.cuda.is_available() else "cpu")
+        if all_files:
+            import re
+
+            with H5Reader(str(filename)) as f:
+                nfiles = int(f.attrs("/Header").get("NumFilesPerSnapshot", 1))
+            m = re.match(r"^(.*)\.(\d+)(\.[^./]+)$", str(filename))
+            if nfiles > 1 and m is None:
+                raise ValueError(f"{filename} belongs to a {nfiles}-file snapshot but is not named <stem>.<i><suffix>")
+            parts = [cls.from_gadget_file(f"{m.group(1)}.{i}{m.group(3)}" if nfiles > 1 else filename,
+                                          ptypes=ptypes, device=device) for i in range(nfiles)]
+            out = parts[0]
+            for p in parts[1:]:
+                out = out + p
+            return out
         fields = OrderedDict()
         particle_types = []
         with H5Reader(str(filename)) as f:

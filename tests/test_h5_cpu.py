@@ -545,3 +545,8 @@ def test_gadget_multi_file_layout(tmp_path):
         parts[0].write_to_gadget_file(tmp_path / "bad.h5", box, shard=(0, 2), shard_counts=counts[:1])
     G = ClusterParticles.from_gadget_file(files[1], device="cpu")
     assert G.num_particles == {"gas": counts[1]["gas"], "dm": counts[1]["dm"]}
+    A = ClusterParticles.from_gadget_file(files[0], device="cpu", all_files=True)
+    S = ClusterParticles.from_gadget_file(tmp_path / "one.h5", device="cpu", all_files=True)
+    assert A.num_particles == S.num_particles
+    for k in S.fields:
+        assert torch.equal(A[k], S[k]), k

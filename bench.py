@@ -11,8 +11,10 @@ density+temperature hydrostatic model, 1e7 DM particles (positions + velocities 
 Eddington f(E) + rejection sampling) plus 1e7 gas particles (positions, zero velocity,
 mass, thermal energy, density) per GPU.  One "step" = one pass of both generators with
 the tables resident in HBM.  Weak scaling: rank k of N generates the k-th contiguous
-index shard of N * 1e7 particles per species; no data-path collective (the only
-collective, an all-reduce of the 16 moment words, is included in the timed region).
+index shard of N * 1e7 particles per species; no data-path collective.  The only
+collective, the sum of the 16 moment words over ranks, is inside the timed region: fused into
+the sampler kernel over peer-mapped buffers (default), or an NCCL all_reduce per step with
+CGB_BENCH_MOMENTS=nccl.
 
 Prints ONE JSON line (rank 0).  Timing: CUDA events on the launching stream, barrier +
 synchronize on both sides, max over ranks.

@@ -21,10 +21,33 @@ from .particles import (  # noqa: F401
 from .peer import PeerMoments  # noqa: F401
 from .radial_profiles import (  # noqa: F401
     RadialProfile,
+    am06_density_profile,
+    am06_temperature_profile,
+    baseline_entropy_profile,
+    beta_model_profile,
+    broken_entropy_profile,
+    constant_profile,
+    convert_nfw_to_hernquist,
+    cored_hernquist_density_profile,
+    cored_snfw_density_profile,
+    cored_snfw_mass_profile,
+    cored_snfw_total_mass,
+    einasto_density_profile,
+    einasto_mass_profile,
     hernquist_density_profile,
+    hernquist_mass_profile,
     nfw_density_profile,
+    nfw_mass_profile,
+    power_law_profile,
+    rescale_profile_by_mass,
+    snfw_conc,
+    snfw_density_profile,
+    snfw_mass_profile,
+    snfw_total_mass,
+    tnfw_density_profile,
     vikhlinin_density_profile,
     vikhlinin_temperature_profile,
+    walker_entropy_profile,
 )
 from .virial import VirialEquilibrium  # noqa: F401
 

@@ -360,3 +360,54 @@ def test_model_helpers_and_flat_files(tmp_path):
     np.testing.assert_allclose(back[:, list(pm.keys()).index("radius")], r, rtol=1e-15)
     head = open(fa).read().splitlines()[:3]
     assert head[0] == "# unit_system=galactic" and "radius" in head[1] and "kpc" in head[2]
+
+
+def test_profile_families_are_self_consistent():
+    """radial_profiles.py:189-762: mass profiles are the integrals of their densities, totals and
+    conversions hold (checked by quadrature, not against copied numbers)."""
+    from scipy.integrate import quad
+
+    import cluster_generator_b200 as cg
+
+    def enclosed(rho, r):
+        return 4.0 * np.pi * quad(lambda x: rho(x) * x * x, 0.0, r, epsabs=0.0, epsrel=1e-11, limit=200)[0]
+
+    M, a = 3.0e14, 400.0
+    for dens, mass in ((cg.snfw_density_profile(M, a), cg.snfw_mass_profile(M, a)),
+                       (cg.cored_snfw_density_profile(M, a, 50.0), cg.cored_snfw_mass_profile(M, a, 50.0)),
+                       (cg.cored_snfw_density_profile(M, a, 900.0), cg.cored_snfw_mass_profile(M, a, 900.0)),
+                       (cg.einasto_density_profile(M, a, 5.0), cg.einasto_mass_profile(M, a, 5.0)),
+                       (cg.hernquist_density_profile(M, a), cg.hernquist_mass_profile(M, a)),
+                       (cg.nfw_density_profile(1.0e7, 100.0), cg.nfw_mass_profile(1.0e7, 100.0))):
+        for r in (30.0, 400.0, 5000.0):
+            assert float(mass(r)) == pytest.approx(enclosed(dens, r), rel=1e-8)
+    assert float(cg.snfw_mass_profile(M, a)(1.0e15)) == pytest.approx(M, rel=1e-5)   # converges like x**-0.5
+    assert float(cg.einasto_mass_profile(M, a, 5.0)(1.0e7)) == pytest.approx(M, rel=1e-6)
+    assert cg.snfw_total_mass(1.0e14, 1000.0, a) * float(cg.snfw_mass_profile(1.0, a)(1000.0)) == pytest.approx(1.0e14)
+    assert cg.cored_snfw_total_mass(1.0e14, 1000.0, a, 50.0) > 1.0e14 and cg.snfw_conc(5.0) == pytest.approx(5.16)
+    # NFW -> Hernquist: same mass inside r_200
+    M200, r200, c = 1.0e15, 2000.0, 4.0
+    M0, ah = cg.convert_nfw_to_hernquist(M200, r200, c)
+    assert float(cg.hernquist_mass_profile(M0, ah)(r200)) == pytest.approx(M200, rel=1e-12)
+    # the cored Hernquist tends to the cuspy one for b -> infinity, and is flat inside a / b
+    r = np.array([1.0, 10.0, 1000.0])
+    np.testing.assert_allclose(cg.cored_hernquist_density_profile(M, a, 1.0e9)(r), cg.hernquist_density_profile(M, a)(r),
+                               rtol=1e-5)
+    core = cg.cored_hernquist_density_profile(M, a, 10.0)
+    assert core(1.0e-3) / core(1.0e-1) == pytest.approx(1.0, abs=5e-3)
+    np.testing.assert_allclose(cg.tnfw_density_profile(1.0e7, 100.0, 1.0e12)(r), cg.nfw_density_profile(1.0e7, 100.0)(r),
+                               rtol=1e-12)
+    assert cg.tnfw_density_profile(1.0e7, 100.0, 500.0)(5000.0) < 0.011 * cg.nfw_density_profile(1.0e7, 100.0)(5000.0)
+    # AM06 gas: density falls, temperature -> T_0 c at the centre
+    assert cg.am06_density_profile(1.0e5, 600.0, 60.0, 0.17, 5.0)(r).tolist() == sorted(
+        cg.am06_density_profile(1.0e5, 600.0, 60.0, 0.17, 5.0)(r).tolist(), reverse=True)
+    assert cg.am06_temperature_profile(8.0, 600.0, 60.0, 0.17)(1.0e-6) == pytest.approx(8.0 * 0.17, rel=1e-6)
+    # entropy families: limits and slopes
+    assert cg.baseline_entropy_profile(10.0, 1000.0, 1500.0, 1.1)(1500.0) == pytest.approx(1010.0)
+    bk = cg.broken_entropy_profile(300.0, 100.0, 0.5)
+    assert np.log(bk(3.0) / bk(0.3)) / np.log(10.0) == pytest.approx(0.5, abs=1e-3)
+    assert np.log(bk(3.0e6) / bk(3.0e5)) / np.log(10.0) == pytest.approx(1.1, abs=1e-3)
+    wk = cg.walker_entropy_profile(1500.0, 4.4, 1.0, 1000.0)
+    assert wk(1500.0) == pytest.approx(1000.0 * 4.4 * np.exp(-1.0)) and wk(6000.0) < wk(1500.0)
+    scaled = cg.rescale_profile_by_mass(cg.beta_model_profile(1.0, 100.0, 0.7), 5.0e13, 1000.0)
+    assert enclosed(scaled, 1000.0) == pytest.approx(5.0e13, rel=1e-7)

@@ -45,6 +45,7 @@ from .radial_profiles import (  # noqa: F401
     snfw_mass_profile,
     snfw_total_mass,
     tnfw_density_profile,
+    tnfw_mass_profile,
     vikhlinin_density_profile,
     vikhlinin_temperature_profile,
     walker_entropy_profile,

@@ -139,6 +139,19 @@ def tnfw_density_profile(rho_s, r_s, r_t):
     return RadialProfile(lambda r: rho_s / ((r / r_s) * (1.0 + r / r_s) ** 2 * (1.0 + (r / r_t) ** 2)))
 
 
+def tnfw_mass_profile(rho_s, r_s, r_t):
+    """Enclosed mass of the truncated NFW profile (radial_profiles.py:339-366 integrates the same
+    integrand symbolically; here by adaptive quadrature per radius)."""
+    from scipy.integrate import quad
+
+    t = r_t / r_s
+
+    def _shape(x):
+        return quad(lambda y: y / ((1.0 + y) ** 2 * (1.0 + (y / t) ** 2)), 0.0, x, epsabs=0.0, epsrel=1e-12)[0]
+
+    return RadialProfile(lambda r: 4.0 * np.pi * rho_s * r_s**3 * np.vectorize(_shape)(np.asarray(r, dtype=np.float64) / r_s))
+
+
 def snfw_density_profile(M, a):
     """"Super-NFW" density, total mass M, scale a (radial_profiles.py:369-386)."""
     norm = 3.0 * M / (16.0 * np.pi * a**3)

@@ -378,6 +378,7 @@ def test_profile_families_are_self_consistent():
                        (cg.cored_snfw_density_profile(M, a, 900.0), cg.cored_snfw_mass_profile(M, a, 900.0)),
                        (cg.einasto_density_profile(M, a, 5.0), cg.einasto_mass_profile(M, a, 5.0)),
                        (cg.hernquist_density_profile(M, a), cg.hernquist_mass_profile(M, a)),
+                       (cg.tnfw_density_profile(1.0e7, 100.0, 800.0), cg.tnfw_mass_profile(1.0e7, 100.0, 800.0)),
                        (cg.nfw_density_profile(1.0e7, 100.0), cg.nfw_mass_profile(1.0e7, 100.0))):
         for r in (30.0, 400.0, 5000.0):
             assert float(mass(r)) == pytest.approx(enclosed(dens, r), rel=1e-8)

@@ -23,7 +23,7 @@ from scipy.interpolate import InterpolatedUnivariateSpline
 
 from . import _native as N
 from .particles import ClusterParticles
-from .utils import G, integrate, integrate_mass, keV, mp, mu, mue, mylog, parse_prng, seed_from_prng, unit_array
+from .utils import _MH_G, _MSUN_G, G, kpc_to_cm, integrate, integrate_mass, keV, mp, mu, mue, mylog, parse_prng, seed_from_prng, unit_array
 from .virial import (PRIVATE_TRIAL_SEED, DeviceSpline, SamplerDiagnostics, SamplerTables,  # noqa: F401
                      VirialEquilibrium, _out_code, radius_cdf_table, shard_bounds)
 
@@ -33,6 +33,7 @@ _UNITS = {
     "total_mass": "Msun", "gas_mass": "Msun", "dark_matter_mass": "Msun", "stellar_mass": "Msun",
     "temperature": "keV", "pressure": "Msun/(Myr**2*kpc)", "gravitational_field": "kpc/Myr**2",
     "gravitational_potential": "kpc**2/Myr**2", "gas_fraction": "",
+    "electron_number_density": "cm**-3", "entropy": "keV*cm**2",
 }
 
 
@@ -233,6 +234,11 @@ class ClusterModel:
 
         if "density" in fields:
             fields["gas_fraction"] = fields["gas_mass"] / fields["total_mass"]
+            # model.py:262-267: n_e = rho / (mue * m_H) in cm**-3 (unyt's number-density
+            # equivalence), entropy = kT * n_e**(-2/3) in keV*cm**2
+            fields["electron_number_density"] = (
+                np.asarray(fields["density"]) * (_MSUN_G / kpc_to_cm**3) / (mue * _MH_G))
+            fields["entropy"] = np.asarray(fields["temperature"]) * fields["electron_number_density"] ** (-2.0 / 3.0)
         return cls(rr.size, fields)
 
     @classmethod

@@ -31,10 +31,13 @@ _M_PER_KPC = 3.0856775809623245e19
 _MP_KG = 1.672621898e-27
 _J_PER_KEV = 1.6021766208e-16
 
-G = _G_MKS * _MSUN_KG * _SEC_PER_MYR**2 / _M_PER_KPC**3  #: kpc**3/Msun/Myr**2
+# unyt's conversion rule: value * old.base_value / new.base_value (tests/_refshim pins it)
+G = _G_MKS * (1.0 / (_MSUN_KG**-1.0 * _SEC_PER_MYR**-2.0 * _M_PER_KPC**3.0))  #: kpc**3/Msun/Myr**2
 mp = _MP_KG / _MSUN_KG  #: Msun
 keV = _J_PER_KEV / _MSUN_KG * _SEC_PER_MYR**2 / _M_PER_KPC**2  #: Msun*kpc**2/Myr**2
 kpc_to_cm = _M_PER_KPC * 100.0
+_MSUN_G = _MSUN_KG * 1.0e3
+_MH_G = 1.007947 * 1.660539040e-27 * 1.0e3  # unyt's mass_hydrogen
 
 X_H = 0.76  # bin/config.yaml: physics.hydrogen_abundance
 mu = 1.0 / (2.0 * X_H + 0.75 * (1.0 - X_H))

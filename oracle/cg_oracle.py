@@ -4,15 +4,15 @@ TEST INFRASTRUCTURE ONLY -- CPU restatement of cluster_generator's particle path
 Bare-ndarray restatement of the reference's Eddington f(E) build, virial check,
 inverse-CDF radius draw and particle assembly, calling the *same* scipy / numpy
 entry points in the *same* order as the reference so that the numbers are the
-reference's numbers by construction.  The reference itself cannot be imported
-(``unyt``, ``h5py`` ... absent; ``opt/*.pyx`` missing from the snapshot), see
-SURVEY.md section 8(c).
+reference's numbers by construction -- and, since round 2, by test: the reference's
+own modules run unmodified behind ``tests/_refshim`` and ``tests/test_reference_cpu.py``
+asserts bitwise equality with this file (see ``oracle/__init__.py``).
 
 Citations are ``file:line`` into the reference tree (``cluster_generator/``).
 
-Parity status: rows D/C/R/E/T/P/Gs exact by construction; row V (the absent
-Cython rejection loop) **parity unpinned**, restated from its call-site
-contract -- see ``oracle/__init__.py``.
+Parity status: rows D/C/R/E/T/P/Gs pinned bitwise to the reference's executed code;
+row V (the absent Cython rejection loop) **parity unpinned**, restated from its
+call-site contract -- see ``oracle/__init__.py``.
 """
 from __future__ import annotations
 
@@ -39,7 +39,8 @@ _M_PER_KPC = 3.0856775809623245e19
 _MP_KG = 1.672621898e-27
 _J_PER_KEV = 1.6021766208e-16
 
-G = _G_MKS * _MSUN_KG * _SEC_PER_MYR**2 / _M_PER_KPC**3  # kpc**3/Msun/Myr**2
+# unyt's conversion rule: value * old.base_value / new.base_value (tests/_refshim pins it)
+G = _G_MKS * (1.0 / (_MSUN_KG**-1.0 * _SEC_PER_MYR**-2.0 * _M_PER_KPC**3.0))  # kpc**3/Msun/Myr**2
 mp = _MP_KG / _MSUN_KG  # Msun
 KEV = _J_PER_KEV / _MSUN_KG * _SEC_PER_MYR**2 / _M_PER_KPC**2  # Msun*kpc**2/Myr**2
 X_H = 0.76  # bin/config.yaml physics.hydrogen_abundance
@@ -464,8 +465,8 @@ def compute_centers_for_binary(center, d, b, a=0.0):
     return center - 0.5 * diff, center + 0.5 * diff
 
 
-def sample_clusters(fields, hses, center, velocity, radii=None, resample=False):
-    """particles.py:587-639 (without passive scalars); ``fields`` is updated in place."""
+def sample_clusters(fields, hses, center, velocity, radii=None, resample=False, passive_scalars=None):
+    """particles.py:587-639; ``fields`` is updated in place."""
     num_halos = len(hses)
     pos = fields["gas", "particle_position"]
     n = pos.shape[0]
@@ -481,6 +482,10 @@ def sample_clusters(fields, hses, center, velocity, radii=None, resample=False):
     d = np.zeros((num_halos, n))
     e = np.zeros((num_halos, n))
     m = np.zeros((num_halos, 3, n))
+    num_scalars = 0
+    if passive_scalars is not None:
+        num_scalars = len(passive_scalars)
+        s = np.zeros((num_halos, num_scalars, n))
     for i, hse in enumerate(hses):
         if "density" not in hse:
             continue
@@ -490,15 +495,22 @@ def sample_clusters(fields, hses, center, velocity, radii=None, resample=False):
         get_energy = InterpolatedUnivariateSpline(hse["radius"], e_arr)
         e[i, :] = get_energy(r[i, :]) * d[i, :]
         m[i, :, :] = np.asarray(velocity[i])[:, np.newaxis] * d[i, :]
+        for j in range(num_scalars):
+            get_scalar = InterpolatedUnivariateSpline(hse["radius"], hse[passive_scalars[j]])
+            s[i, j, :] = get_scalar(r[i, :]) * d[i, :]
     dens = d.sum(axis=0)
     eint = e.sum(axis=0) / dens
     mom = m.sum(axis=0) / dens
+    if num_scalars > 0:
+        ps = s.sum(axis=0) / dens
     if resample:
         vol = fields["gas", "particle_mass"] / fields["gas", "density"]
         fields["gas", "particle_mass"][idxs] = dens[idxs] * vol[idxs]
     fields["gas", "density"][idxs] = dens[idxs]
     fields["gas", "thermal_energy"][idxs] = eint[idxs]
     fields["gas", "particle_velocity"][idxs] = mom.T[idxs]
+    for j in range(num_scalars):
+        fields["gas", passive_scalars[j]][idxs] = ps[j, idxs]
     return fields
 
 

@@ -97,6 +97,7 @@ SYMBOLS = [
                                         c_int, c_void_p, c_int64, c_uint64, c_int64, c_void_p,
                                         c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
     ("cgb_sample_gas", c_int, [POINTER(SampleArgs), c_void_p, c_void_p, c_void_p]),
+    ("cgb_screen_audit", c_int, [c_void_p, c_int64, c_int64, c_uint64, c_int64, c_void_p, c_void_p]),
     ("cgb_ppform_workspace_bytes", c_size_t, [c_int]),
     ("cgb_ppform_prepare", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     ("cgb_map_field", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,

@@ -675,8 +675,9 @@ static size_t edd_smem_bytes(int n)
 
 extern "C" size_t cgb_eddington_workspace_bytes(int n)
 {
-    // t_rho (n+4), c_rho (n), wrk (n), t_g (n+4), c_g (n), wrk_g (n), fit scratch 6n
-    return n > 0 ? (size_t)(12 * (size_t)n + 8) * sizeof(double) : 0;
+    // t_rho (n+4), c_rho (n), wrk (n), t_g (n+4), c_g (n), wrk_g (n), fit scratch 17n
+    // (the three fits share one Givens factorisation of the energy grid)
+    return n > 0 ? (size_t)(23 * (size_t)n + 8) * sizeof(double) : 0;
 }
 
 extern "C" int cgb_eddington_df(const double* d_ee, const double* d_pden, int n, double epsabs,
@@ -705,7 +706,7 @@ extern "C" int cgb_eddington_df(const double* d_ee, const double* d_pden, int n,
     void* fit_scratch = w;
     int rc;
     // density_spline = IUS(ee, pden)                                  (virial.py:45)
-    if ((rc = cgb_launch_spline_fit(d_ee, d_pden, n, t_rho, c_rho, fit_scratch, s, fit_method))) return rc;
+    if ((rc = cgb_launch_spline_fit(d_ee, d_pden, n, t_rho, c_rho, fit_scratch, s, fit_method, 0))) return rc;
     if ((rc = cgb_launch_splder_coeffs(t_rho, c_rho, n, wrk, s))) return rc;
     const size_t smem = edd_smem_bytes(n);
     CGB_REQUIRE(smem <= 227 * 1024, "cgb_eddington_df: n = %d needs %zu B of shared memory", n, smem);
@@ -715,13 +716,13 @@ extern "C" int cgb_eddington_df(const double* d_ee, const double* d_pden, int n,
         d_ee, n, t_rho, wrk, epsabs, epsrel, d_g, d_last, d_ier);
     CGB_CUDA_CHECK(cudaGetLastError());
     // g_spline = IUS(ee, g); ff = g_spline(ee, 1) / (sqrt(8) pi^2)    (virial.py:65-66)
-    if ((rc = cgb_launch_spline_fit(d_ee, d_g, n, t_g, c_g, fit_scratch, s, fit_method))) return rc;
+    if ((rc = cgb_launch_spline_fit(d_ee, d_g, n, t_g, c_g, fit_scratch, s, fit_method, fit_method == CGB_FIT_FITPACK))) return rc;
     if ((rc = cgb_launch_splder_coeffs(t_g, c_g, n, wrk_g, s))) return rc;
     const double den = sqrt(8.0) * (M_PI * M_PI);
     cgb_ff_kernel<<<(n + 255) / 256, 256, 0, s>>>(t_g, wrk_g, n, d_ee, den, d_ff);
     CGB_CUDA_CHECK(cudaGetLastError());
     // self.f = IUS(ee, ff)                                            (virial.py:67)
-    if ((rc = cgb_launch_spline_fit(d_ee, d_ff, n, d_f_t, d_f_c, fit_scratch, s, fit_method))) return rc;
+    if ((rc = cgb_launch_spline_fit(d_ee, d_ff, n, d_f_t, d_f_c, fit_scratch, s, fit_method, fit_method == CGB_FIT_FITPACK))) return rc;
     return CGB_OK;
 }
 

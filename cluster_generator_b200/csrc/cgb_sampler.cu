@@ -1298,6 +1298,29 @@ static int launch_sample(const SampleParams& sp, cudaStream_t s)
 // ---------------------------------------------------------------------------
 // gas / tracer kernel and the sub_sample assembly kernel (elementwise, HBM-bound)
 // ---------------------------------------------------------------------------
+// Two consecutive particles per thread: their independent chains interleave (the table
+// walks are latency-bound) and every plane takes ONE 16-byte (fp64) / 8-byte (fp32) store
+// per pair instead of two scalar ones.  The velocities of gas and tracer particles are
+// identically zero (model.py:829-831, 933-935): they are written as vector stores of
+// zeros, or not at all when the caller passes d_vel == NULL for storage it zeroed itself.
+template <typename OutT> struct Pair2;
+template <> struct Pair2<double> { typedef double2 type; };
+template <> struct Pair2<float> { typedef float2 type; };
+
+template <typename OutT>
+__device__ __forceinline__ void store_pair(void* p, long long i, double a, double b, bool both, bool vec)
+{
+    typedef typename Pair2<OutT>::type V;
+    if (vec && both) {
+        V v;
+        v.x = (OutT)a; v.y = (OutT)b;
+        *(V*)((OutT*)p + i) = v;
+    } else {
+        ((OutT*)p)[i] = (OutT)a;
+        if (both) ((OutT*)p)[i + 1] = (OutT)b;
+    }
+}
+
 template <typename OutT, bool HOST_U>
 __global__ void __launch_bounds__(256) cgb_gas_kernel(const __grid_constant__ SampleParams p, void* aux0, void* aux1)
 {
@@ -1316,59 +1339,104 @@ __global__ void __launch_bounds__(256) cgb_gas_kernel(const __grid_constant__ Sa
     const double* const ps_brk = p.base + hdr->off_psi_brk;
     const double* const ps_pp = p.base + hdr->off_psi_pp;
     const long long n_local = p.id_end - p.id_begin;
+    const long long n_pairs = (n_local + 1) >> 1;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long loc = (long long)blockIdx.x * blockDim.x + threadIdx.x; loc < n_local; loc += stride) {
-        const unsigned long long id = (unsigned long long)(p.id_begin + loc);
-        // sub_sample: np.tile(radius_sub, s)[:n]                       (model.py:887-890)
-        const unsigned long long rid = p.radius_period > 0 ? id % (unsigned long long)p.radius_period : id;
-        double u, uc, up;
-        if (HOST_U && p.hu.d_u_r) u = p.hu.d_u_r[p.radius_period > 0 ? (long long)rid : loc];
-        else {
-            const Philox4 w = philox_rk(p.rk, (unsigned)rid, (unsigned)(rid >> 32), 0u, CGB_STREAM_RADIUS);
-            u = u52(w.x, w.y);
+    // vector stores need even plane strides and 2-element aligned bases
+    const size_t amask = 2 * sizeof(OutT) - 1;
+    const bool vec = ((p.ld & 1) == 0) && (((size_t)p.pos | (size_t)p.vel | (size_t)p.mass | (size_t)p.pot |
+                                            (size_t)aux0 | (size_t)aux1) & amask) == 0;
+    for (long long pr = (long long)blockIdx.x * blockDim.x + threadIdx.x; pr < n_pairs; pr += stride) {
+        const long long loc = 2 * pr;
+        const bool both = loc + 1 < n_local;
+        double u[2], uc[2], up[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const long long lq = both ? loc + q : loc;  // the odd tail computes particle `loc` twice
+            const unsigned long long id = (unsigned long long)(p.id_begin + lq);
+            // sub_sample: np.tile(radius_sub, s)[:n]                   (model.py:887-890)
+            const unsigned long long rid = p.radius_period > 0 ? id % (unsigned long long)p.radius_period : id;
+            if (HOST_U && p.hu.d_u_r) u[q] = p.hu.d_u_r[p.radius_period > 0 ? (long long)rid : lq];
+            else {
+                const Philox4 w = philox_rk(p.rk, (unsigned)rid, (unsigned)(rid >> 32), 0u, CGB_STREAM_RADIUS);
+                u[q] = u52(w.x, w.y);
+            }
+            if (HOST_U && p.hu.d_u_ct) { uc[q] = p.hu.d_u_ct[lq]; up[q] = p.hu.d_u_ph[lq]; }
+            else {
+                const Philox4 w = philox_rk(p.rk, (unsigned)id, (unsigned)(id >> 32), 0u, CGB_STREAM_POS_DIR);
+                uc[q] = u52(w.x, w.y); up[q] = u52(w.z, w.w);
+            }
         }
-        if (HOST_U && p.hu.d_u_ct) { uc = p.hu.d_u_ct[loc]; up = p.hu.d_u_ph[loc]; }
-        else {
-            const Philox4 w = philox_rk(p.rk, (unsigned)id, (unsigned)(id >> 32), 0u, CGB_STREAM_POS_DIR);
-            uc = u52(w.x, w.y); up = u52(w.z, w.w);
+        // bucket table + short search for np.interp's interval (same rule as the DM sampler);
+        // the two searches advance together
+        int lo[2], hi[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const unsigned lh = __ldg(cdf_lut + cdf_bucket(u[q]));
+            lo[q] = (int)(lh & 0xffffu); hi[q] = (int)(lh >> 16);
         }
-        // bucket table + short search for np.interp's interval (same rule as the DM sampler)
-        const unsigned lh = __ldg(cdf_lut + cdf_bucket(u));
-        int lo = (int)(lh & 0xffffu), hi = (int)(lh >> 16);
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (__ldg(cdf_P + mid) <= u) lo = mid; else hi = mid - 1;
+        while (lo[0] < hi[0] || lo[1] < hi[1]) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (lo[q] < hi[q]) {
+                    const int mid = (lo[q] + hi[q] + 1) >> 1;
+                    if (__ldg(cdf_P + mid) <= u[q]) lo[q] = mid; else hi[q] = mid - 1;
+                }
+            }
         }
-        const double r = __dadd_rn(__dmul_rn(__ldg(cdf_s + lo), __dsub_rn(u, __ldg(cdf_P + lo))),
-                                   __ldg(cdf_r + lo));
-        const int iv = __ldg(cdf_iv + lo).x;  // starting piece for every spline over `radius`
-        const double ct = __dadd_rn(-1.0, __dmul_rn(2.0, uc));
-        const double st = sqrt(__dmul_rn(__dsub_rn(1.0, ct), __dadd_rn(1.0, ct)));
-        double sp, cp;
-        sincos2pi(up, &sp, &cp);
-        const double rs = __dmul_rn(r, st);
-        store_out<OutT>(p.pos, loc, __dmul_rn(rs, cp));
-        store_out<OutT>(p.pos, p.ld + loc, __dmul_rn(rs, sp));
-        store_out<OutT>(p.pos, 2 * p.ld + loc, __dmul_rn(r, ct));
+        double r[2], px[2], py[2], pz[2];
+        int jw[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            r[q] = __dadd_rn(__dmul_rn(__ldg(cdf_s + lo[q]), __dsub_rn(u[q], __ldg(cdf_P + lo[q]))),
+                             __ldg(cdf_r + lo[q]));
+            jw[q] = __ldg(cdf_iv + lo[q]).x;  // starting piece for every spline over `radius`
+            const double ct = __dadd_rn(-1.0, __dmul_rn(2.0, uc[q]));
+            const double st = sqrt(__dmul_rn(__dsub_rn(1.0, ct), __dadd_rn(1.0, ct)));
+            double sp, cp;
+            sincos2pi(up[q], &sp, &cp);
+            const double rs = __dmul_rn(r[q], st);
+            px[q] = __dmul_rn(rs, cp); py[q] = __dmul_rn(rs, sp); pz[q] = __dmul_rn(r[q], ct);
+        }
+        store_pair<OutT>(p.pos, loc, px[0], px[1], both, vec);
+        store_pair<OutT>(p.pos, p.ld + loc, py[0], py[1], both, vec);
+        store_pair<OutT>(p.pos, 2 * p.ld + loc, pz[0], pz[1], both, vec);
         if (p.vel) {
-            store_out<OutT>(p.vel, loc, 0.0);
-            store_out<OutT>(p.vel, p.ld + loc, 0.0);
-            store_out<OutT>(p.vel, 2 * p.ld + loc, 0.0);
+            store_pair<OutT>(p.vel, loc, 0.0, 0.0, both, vec);
+            store_pair<OutT>(p.vel, p.ld + loc, 0.0, 0.0, both, vec);
+            store_pair<OutT>(p.vel, 2 * p.ld + loc, 0.0, 0.0, both, vec);
         }
-        if (p.mass) store_out<OutT>(p.mass, loc, p.particle_mass);
+        if (p.mass) store_pair<OutT>(p.mass, loc, p.particle_mass, p.particle_mass, both, vec);
         // the splines normally share the radius knots: each walk starts at the previous
         // answer and only verifies it (pp_walk corrects it if the knots differ)
-        int jw = iv;
         if (aux0) {
-            jw = pp_walk(a0_brk, nai, jw, r);
-            store_out<OutT>(aux0, loc, pp_eval_at(a0_brk, a0_pp, jw, r));
+            double v[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                jw[q] = pp_walk(a0_brk, nai, jw[q], r[q]);
+                v[q] = pp_eval_at(a0_brk, a0_pp, jw[q], r[q]);
+            }
+            store_pair<OutT>(aux0, loc, v[0], v[1], both, vec);
         }
         if (aux1) {
-            jw = pp_walk(a1_brk, nai, jw, r);
-            store_out<OutT>(aux1, loc, pp_eval_at(a1_brk, a1_pp, jw, r));
+            double v[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                jw[q] = pp_walk(a1_brk, nai, jw[q], r[q]);
+                v[q] = pp_eval_at(a1_brk, a1_pp, jw[q], r[q]);
+            }
+            store_pair<OutT>(aux1, loc, v[0], v[1], both, vec);
         }
-        if (p.pot) store_out<OutT>(p.pot, loc, -pp_eval_at(ps_brk, ps_pp, pp_walk(ps_brk, npi, jw, r), r));
-        if (p.radius) p.radius[loc] = r;
+        if (p.pot) {
+            double v[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+                v[q] = -pp_eval_at(ps_brk, ps_pp, pp_walk(ps_brk, npi, jw[q], r[q]), r[q]);
+            store_pair<OutT>(p.pot, loc, v[0], v[1], both, vec);
+        }
+        if (p.radius) {
+            p.radius[loc] = r[0];
+            if (both) p.radius[loc + 1] = r[1];
+        }
     }
 }
 
@@ -1579,7 +1647,7 @@ extern "C" int cgb_sample_gas(const cgb_sample_args* args, void* d_aux_out0, voi
     const long long n_local = sp.id_end - sp.id_begin;
     if (n_local == 0) return CGB_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    const unsigned blocks = (unsigned)min((n_local + 255) / 256, 148LL * 16);
+    const unsigned blocks = (unsigned)min(((n_local + 1) / 2 + 255) / 256, 148LL * 16);
     const bool f32 = args->out_dtype == CGB_DTYPE_F32, hu = any_host_u(args->hu);
     if (f32) {
         if (hu) cgb_gas_kernel<float, true><<<blocks, 256, 0, s>>>(sp, d_aux_out0, d_aux_out1);
@@ -1588,6 +1656,101 @@ extern "C" int cgb_sample_gas(const cgb_sample_args* args, void* d_aux_out0, voi
         if (hu) cgb_gas_kernel<double, true><<<blocks, 256, 0, s>>>(sp, d_aux_out0, d_aux_out1);
         else cgb_gas_kernel<double, false><<<blocks, 256, 0, s>>>(sp, d_aux_out0, d_aux_out1);
     }
+    CGB_CUDA_CHECK(cudaGetLastError());
+    return CGB_OK;
+}
+
+// ---- screen audit (diagnostics / tests) --------------------------------------
+// Every trial of every particle in [id_begin, id_end) is evaluated BOTH by the fp32 interval
+// screen (screen_trial, the function and table the production kernel uses, with the same
+// per-particle fp32 inputs) and by the exact fp64 test, in the production kernel's trial
+// order (Philox counter (id, pair), two trials per call), until the exact test accepts or
+// max_trials is reached.  A contradiction -- the screen rejects what the exact test accepts
+// or accepts what it rejects -- would mean the screen changed a decision; the claim
+// "identical to the exact evaluation" holds iff counts[2] stays 0.
+//   counts[0] trials audited   [1] undecided by the screen   [2] CONTRADICTIONS
+//   [3] particles stopped at max_trials   [4] screen accepts   [5] screen rejects
+//   [6] particles whose screen is disabled (es = NaN)   [7] sum of accepted trial numbers
+__global__ void __launch_bounds__(256) cgb_screen_audit_kernel(const __grid_constant__ SampleParams p,
+                                                               unsigned long long* __restrict__ counts,
+                                                               long long max_trials)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    float2* s_screen = (float2*)smem;
+    __shared__ unsigned long long s_mbar;
+    __shared__ unsigned long long s_cnt[8];
+    Tables T;
+    load_tables(p.base, T);
+    if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
+    load_screen(p.base, s_screen, &s_mbar);
+    __syncthreads();
+    unsigned long long c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long n_local = p.id_end - p.id_begin;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long loc = (long long)blockIdx.x * blockDim.x + threadIdx.x; loc < n_local; loc += stride) {
+        const unsigned long long id = (unsigned long long)(p.id_begin + loc);
+        // phase 0 of cgb_sample_kernel
+        const Philox4 wr = philox_rk(p.rk, (unsigned)id, (unsigned)(id >> 32), 0u, CGB_STREAM_RADIUS);
+        const double u = u52(wr.x, wr.y);
+        const int j = cdf_find(T, u);
+        const double r = __dadd_rn(__dmul_rn(__ldg(T.cdf_s + j), __dsub_rn(u, __ldg(T.cdf_P + j))), __ldg(T.cdf_r + j));
+        const int2 iv = __ldg(T.cdf_iv + j);
+        const double psi = pp_eval_at(T.psi_brk, T.psi_pp, pp_walk(T.psi_brk, T.n_psi_int, iv.x, r), r);
+        const double ve2 = __dmul_rn(2.0, psi);
+        const double env = __dmul_rn(ve2, pp_eval_at(T.f_brk, T.f_pp, pp_walk(T.f_brk, T.n_f_int, iv.y, psi), psi));
+        const double vesc = sqrt(ve2);
+        const float ps = (float)psi, vs = (float)(vesc * 0x1.0p-32);
+        const float es = screen_es(psi, vesc, env, T.f_scale);
+        if (es != es) ++c[6];
+        long long t = 0;
+        bool done = false;
+        for (unsigned pair = 0; !done && t < max_trials; ++pair) {
+            const Philox4 w = philox_rk(p.rk, (unsigned)id, (unsigned)(id >> 32), pair, CGB_STREAM_VEL_TRIAL);
+#pragma unroll
+            for (int h = 0; h < 2 && !done; ++h) {
+                const unsigned wa = h ? w.z : w.x, wb = h ? w.w : w.y;
+                const int sc = screen_trial(s_screen, T.inv_w_f, wa, wb, ps, vs, es);
+                double v2;
+                const bool ex = exact_accept(T, u32_to_double(wa) * 0x1.0p-32, u32_to_double(wb) * 0x1.0p-32,
+                                             psi, vesc, env, v2);
+                ++t;
+                ++c[0];
+                if (sc == 2) ++c[1];
+                else if ((sc == 1) != ex) ++c[2];
+                if (sc == 1) ++c[4];
+                if (sc == 0) ++c[5];
+                if (ex) { done = true; c[7] += (unsigned long long)t; }
+            }
+        }
+        if (!done) ++c[3];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        unsigned long long v = c[k];
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_cnt[k], v);
+    }
+    __syncthreads();
+    if (threadIdx.x < 8 && s_cnt[threadIdx.x]) atomicAdd(counts + threadIdx.x, s_cnt[threadIdx.x]);
+}
+
+extern "C" int cgb_screen_audit(const void* d_workspace, int64_t id_begin, int64_t id_end, uint64_t seed,
+                                int64_t max_trials, unsigned long long* d_counts, void* stream)
+{
+    CGB_REQUIRE(d_workspace && d_counts, "cgb_screen_audit: null pointer");
+    CGB_REQUIRE(id_end >= id_begin && id_begin >= 0 && max_trials > 0, "cgb_screen_audit: bad range or trial cap");
+    if (id_end == id_begin) return CGB_OK;
+    SampleParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.base = (const double*)d_workspace;
+    sp.id_begin = id_begin; sp.id_end = id_end;
+    set_round_keys(sp, seed);
+    int dev = 0, sms = 0;
+    CGB_CUDA_CHECK(cudaGetDevice(&dev));
+    CGB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CGB_CUDA_CHECK(cudaFuncSetAttribute(cgb_screen_audit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)SCREEN_BYTES));
+    cgb_screen_audit_kernel<<<sms * 6, 256, SCREEN_BYTES, (cudaStream_t)stream>>>(sp, d_counts, (long long)max_trials);
     CGB_CUDA_CHECK(cudaGetLastError());
     return CGB_OK;
 }

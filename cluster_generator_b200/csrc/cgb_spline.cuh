@@ -2,9 +2,10 @@
 #pragma once
 #include <cuda_runtime.h>
 
-// d_work: n*6 doubles (band[n][5], rhs[n])
+// d_work: n*17 doubles.  reuse_factor = 1: d_work still holds the Givens factorisation of a
+// previous CGB_FIT_FITPACK fit over the SAME x (only the right-hand side is processed).
 int cgb_launch_spline_fit(const double* d_x, const double* d_y, int n, double* d_t, double* d_c,
-                          void* d_work, cudaStream_t s, int method);
+                          void* d_work, cudaStream_t s, int method, int reuse_factor);
 // d_wrk: n-1 doubles
 int cgb_launch_splder_coeffs(const double* d_t, const double* d_c, int n, double* d_wrk, cudaStream_t s);
 // d_brk: n-2 doubles, d_pp: (n-3)*4 doubles

@@ -335,6 +335,13 @@ class ClusterModel:
         if name in self.fields:
             mylog.warning("Overwriting field %s." % name)
         self.fields[name] = unit_array(value, _UNITS.get(name, ""))
+        # The reference rebuilds its CDF and splines from self.fields on every generate_* call
+        # (virial.py:148-166, model.py:879-930) while a VirialEquilibrium keeps the f(E) it was
+        # built with: drop the cached device tables, keep the virial objects.
+        self._gas_tables.clear()
+        for vir in (self._dm_virial, self._star_virial):
+            if vir is not None:
+                vir._tables.clear()
 
     def find_field_at_radius(self, field, r):
         """model.py:658-665"""

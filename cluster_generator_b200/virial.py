@@ -315,6 +315,20 @@ class VirialEquilibrium:
             self._tables[key] = SamplerTables(P_r, r_cdf, mtot, psi_spline, self.f)
         return self._tables[key]
 
+    def screen_audit(self, num_particles, r_max=None, seed=0, max_trials=1 << 20, first_id=0):
+        """Diagnostics: run the fp32 interval screen and the exact fp64 accept test side by
+        side on EVERY trial of ``num_particles`` particles (``cgb_screen_audit``) and return
+        the counters as a dict; ``contradictions`` must be 0."""
+        dev = N.require_cuda()
+        tabs = self.sampler_tables(r_max)
+        counts = torch.zeros(8, dtype=torch.int64, device=dev)
+        N.check(N.lib().cgb_screen_audit(N.ptr(tabs.workspace), int(first_id), int(first_id) + int(num_particles),
+                                         int(seed) & 0xFFFFFFFFFFFFFFFF, int(max_trials), N.ptr(counts),
+                                         N.stream_ptr()))
+        names = ("trials", "undecided", "contradictions", "capped_particles", "screen_accepts",
+                 "screen_rejects", "screen_disabled_particles", "sum_accepted_trials")
+        return dict(zip(names, (int(v) for v in counts.cpu())))
+
     def generate_particles(
         self,
         num_particles,
@@ -470,7 +484,9 @@ class VirialEquilibrium:
             fields[key, "particle_potential"] = pot
         diag = {}
         if moments is not None:
-            diag[key] = SamplerDiagnostics(moments, shard, reduced=peer_slot is not None)
+            # sub_sample > 1: every rank draws the whole sub-sample, so its moments already are
+            # the global ones (summing them over ranks would count the sub-sample world times)
+            diag[key] = SamplerDiagnostics(moments, shard, reduced=peer_slot is not None or sub_sample > 1)
         del keep
         return ClusterParticles(key, fields, diag)
 

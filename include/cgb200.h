@@ -240,6 +240,16 @@ size_t cgb_sample_scratch_bytes(void);
 int cgb_sample_particles(const cgb_sample_args *args, void *d_scratch, size_t scratch_bytes,
                          void *stream);
 
+/* Screen audit (diagnostics): runs the fp32 interval screen AND the exact fp64 accept test on
+ * every trial of particles [id_begin, id_end) of a prepared DM/star sampler, in the production
+ * kernel's trial order, up to max_trials per particle.  d_counts: uint64[8], ACCUMULATED
+ * (caller zeroes): [0] trials  [1] undecided by the screen  [2] contradictions (must stay 0:
+ * the screen never changes a decision of virial.py:198-206's accept test)  [3] particles that
+ * hit max_trials  [4] screen accepts  [5] screen rejects  [6] particles with the screen
+ * disabled  [7] sum of accepted trial numbers (== moments[1] when [3] == 0). */
+int cgb_screen_audit(const void *d_workspace, int64_t id_begin, int64_t id_end, uint64_t seed,
+                     int64_t max_trials, unsigned long long *d_counts, void *stream);
+
 /* Directions-only pass used for sub_sample > 1 (virial.py:170-176,208-223): particle
  * i takes radius/speed d_radius_sub[i % n_sub], d_speed_sub[i % n_sub] and fresh
  * directions; d_psi_sub (nullable) feeds the potential. */
@@ -264,7 +274,8 @@ int cgb_generate_velocities(const double *d_psi, const double *d_vesc, const dou
 /* Gs: replaces the numeric part of ClusterModel.generate_gas_particles
  * (model.py:838-947) and generate_tracer_particles (model.py:766-836): radius from
  * the gas-mass CDF, isotropic position, aux splines (thermal energy, density) and
- * optional potential at the radius; velocity planes are zero-filled when d_vel != NULL.
+ * optional potential at the radius; velocity planes are zero-filled when d_vel != NULL
+ * (d_vel == NULL: the caller owns zeroed storage).  Two particles per thread, 16-byte stores.
  * d_aux_out[k]: nullable f64/f32 arrays (out_dtype) for aux spline k. */
 int cgb_sample_gas(const cgb_sample_args *args, void *d_aux_out0, void *d_aux_out1, void *stream);
 

@@ -16,6 +16,13 @@ collective, the sum of the 16 moment words over ranks, is inside the timed regio
 the sampler kernel over peer-mapped buffers (default), or an NCCL all_reduce per step with
 CGB_BENCH_MOMENTS=nccl.
 
+`e2e` is the same metric through the public API with host tables in and pinned host arrays
+out (generate_*_particles(host=True): chunked generation, D2H copies overlapped with the
+kernels), graded against a concurrent pinned-D2H ceiling measured in the same run
+(`e2e.roofline`).  `configs` carries the other BASELINE configs at their stated sizes
+(configs[0] 1e5 Hernquist + CPU oracle, configs[2] NFW+BCG at 1e8 and 1e9 through ClusterICs
+over the N ranks, configs[3] binary merger + HDF5 write at N = 1, configs[4] sweep).
+
 Prints ONE JSON line (rank 0).  Timing: CUDA events on the launching stream, barrier +
 synchronize on both sides, max over ranks.
 """
@@ -37,8 +44,23 @@ METRIC = "particles/sec (pos+vel, device-timed)"
 UNIT = "particles/s"
 F_FIXED, F_TRIAL = 200.0, 52.0   # algorithmic flop per DM particle = 200 + 52 * T
 B_DM, B_GAS = 56.0, 72.0         # algorithmic bytes written per particle (fp64)
-NCU_WARP_INSTR_PER_LAUNCH = 5.323e8  # smsp__inst_executed.sum of the same capture (1e7 Vikhlinin DM particles)
-NCU_DRAM_BYTES_PER_LAUNCH = 509.5e6  # 1.8 MB read + 507.7 MB written (algorithmic: 560 MB, part still in L2)
+NCU_PROFILE = os.path.join(ROOT, "profiles", "r02_ncu.json")  # written by scripts/make_profiles.py
+SAMPLER_SRC = os.path.join(ROOT, "cluster_generator_b200", "csrc", "cgb_sampler.cu")
+
+
+def load_ncu_profile():
+    """Per-launch ncu counters of the dominant kernel on THIS workload (smsp__inst_executed,
+    dram bytes), captured by scripts/make_profiles.py together with the sha256 of the kernel
+    source they were measured on; `stale` when the source has changed since."""
+    import hashlib
+
+    try:
+        prof = json.load(open(NCU_PROFILE))
+    except Exception:
+        return None
+    sha = hashlib.sha256(open(SAMPLER_SRC, "rb").read()).hexdigest()
+    prof["stale"] = prof.get("sampler_sha256") != sha
+    return prof
 
 
 def build_product_model():
@@ -230,6 +252,168 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------- #
+# the other BASELINE configs, measured at their stated sizes
+# --------------------------------------------------------------------------- #
+def run_configs(args, rank, world, dev, barrier):
+    """configs[0] (1e5 Hernquist DM, with the CPU oracle at the same size), configs[2] (NFW DM +
+    BCG stars through ClusterICs at 1e8 and at the north-star size 1e9, sharded over the N
+    ranks), configs[3] (binary merger incl. the HDF5 write; N = 1 only) and the configs[4]
+    sweep (1e6 ... 1e9 Hernquist DM particles).  Device-timed (CUDA events, max over ranks,
+    best of 3 after one warm-up call) plus the wall clock of the same call."""
+    import shutil
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import cluster_generator_b200 as cg
+    from cluster_generator_b200 import _native as N
+
+    f64 = torch.float64
+    dfma = N.ctypes.c_double()
+    N.check(N.lib().cgb_measure_dfma_tflops(4096, N.ctypes.byref(dfma), N.stream_ptr()))
+
+    def timed(fn, reps=3):
+        res = fn()
+        best = (float("inf"), float("inf"))
+        for _ in range(reps):
+            del res
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            w0 = time.perf_counter()
+            e0.record()
+            res = fn()
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1), 1e3 * (time.perf_counter() - w0)], dtype=f64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            best = min(best, (float(t[0]), float(t[1])))
+        return res, best[0], best[1]
+
+    def species(p, key, n, ms):
+        d = p.diagnostics[key].all_reduce().as_dict()
+        flops = F_FIXED + F_TRIAL * d["mean_trials"]
+        return {"particles": n, "device_ms": ms, "particles_per_s": n / (ms * 1e-3), "mean_trials": d["mean_trials"],
+                "max_trials": d["max_trials"], "failures": d["failures"],
+                "fp64_roofline_frac": n * flops / (ms * 1e-3) / 1e12 / dfma.value}
+
+    out = {"note": "device_ms: CUDA events around the public-API call, max over ranks, best of 3; "
+                   "wall_ms: barrier-to-barrier host clock of the same call",
+           "n_gpus": world, "dfma_peak_tflops": dfma.value}
+    shard = (rank, world)
+
+    # ---- configs[0]: Hernquist DM-only, 1e5 DM particles, and the reference CPU path at that size
+    m1 = cg.ClusterModel.no_gas(0.1, 1.0e4, cg.hernquist_density_profile(1.0e15, 500.0))
+    m1.dm_virial
+    n1 = 100_000
+    p, ms, wall = timed(lambda: m1.generate_dm_particles(n1, prng=25, shard=shard))
+    c1 = species(p, "dm", n1, ms)
+    c1["wall_ms"] = wall
+    if rank == 0:
+        from oracle import cg_oracle as O
+
+        om = O.no_gas(0.1, 1.0e4, O.hernquist_density_profile(1.0e15, 500.0))
+        om.dm_virial
+        t0 = time.perf_counter()
+        om.dm_virial.generate_particles(n1, prng=25)
+        c1["cpu_oracle_s"] = time.perf_counter() - t0
+        c1["cpu_oracle_particles_per_s"] = n1 / c1["cpu_oracle_s"]
+        c1["cpu_oracle_what"] = "oracle mode A (sequential C loop + numpy), 1 core, same size"
+    out["config1_hernquist_1e5"] = c1
+    del p
+
+    # ---- configs[4]: sweep 1e6 ... 1e9 Hernquist DM particles over the N ranks (strong scaling in n_gpus)
+    sweep = []
+    for n in (1_000_000, 10_000_000, 100_000_000, 1_000_000_000):
+        p, ms, wall = timed(lambda: m1.generate_dm_particles(n, prng=7, shard=shard))
+        r = species(p, "dm", n, ms)
+        r["wall_ms"] = wall
+        sweep.append(r)
+        del p
+        torch.cuda.empty_cache()
+    out["config5_sweep_hernquist_dm"] = sweep
+
+    # ---- configs[2] (headline): NFW DM + Hernquist BCG stars through ClusterICs, split like ics.py:132-153
+    star = cg.hernquist_density_profile(1.0e12, 20.0)
+    m3 = cg.ClusterModel.no_gas(0.1, 1.0e4, cg.nfw_density_profile(1.0e7, 100.0) + star, stellar_density=star)
+    m3.dm_virial, m3.star_virial
+    mdm, mst = float(m3["dark_matter_mass"].d[-1]), float(m3["stellar_mass"].d[-1])
+    c3 = []
+    for ntot in (100_000_000, 1_000_000_000):
+        nst = int(np.rint(ntot * mst / (mdm + mst)))   # equal-mass particles
+        ndm = ntot - nst
+        ics = cg.ClusterICs("c3", 1, [m3], [0.0, 0.0, 0.0], [0.0, 0.0, 0.0],
+                            num_particles={"dm": ndm, "star": nst}, r_max=1.0e4)
+        p, ms, wall = timed(lambda: ics.setup_particle_ics(prng=11, shard=shard))
+        r = {"total_particles": ntot, "device_ms": ms, "wall_ms": wall, "particles_per_s": ntot / (ms * 1e-3),
+             "what": "ClusterICs.setup_particle_ics(shard=(rank, N)): DM + star particles, positions + velocities + masses"}
+        del p
+        torch.cuda.empty_cache()
+        pd, msd, _ = timed(lambda: m3.generate_dm_particles(ndm, r_max=1.0e4, prng=11, shard=shard))
+        r["dm"] = species(pd, "dm", ndm, msd)
+        del pd
+        torch.cuda.empty_cache()
+        ps, mss, _ = timed(lambda: m3.generate_star_particles(nst, r_max=1.0e4, prng=12, shard=shard))
+        r["star"] = species(ps, "star", nst, mss)
+        del ps
+        if ntot == 1_000_000_000:
+            r["north_star_target"] = {"target": ">= 1e9 DM+star particles in < 10 s on 8 x B200",
+                                      "wall_s": wall * 1e-3, "n_gpus": world, "met": wall * 1e-3 < 10.0}
+        c3.append(r)
+        torch.cuda.empty_cache()
+    out["config3_nfw_bcg"] = c3
+
+    # ---- configs[3]: 1:3 binary merger, 1e8 DM + 1e8 gas split by mass, written to HDF5 (N = 1 only)
+    if world == 1 and os.environ.get("CGB_BENCH_CONFIG4", "1") == "1":
+        vd = dict(r_c=100.0, r_s=1000.0, alpha=1.0, beta=0.67, epsilon=3.0)
+        vt = dict(a=0.0, b=2.0, c=1.0, r_t=1500.0, r_cool=80.0, a_cool=1.0)
+        ma = cg.ClusterModel.from_dens_and_temp(0.1, 1.0e4, cg.vikhlinin_density_profile(rho_0=4.2e5, **vd),
+                                                cg.vikhlinin_temperature_profile(T_0=10.0, T_min=6.0, **vt),
+                                                integrator="device")
+        mb = cg.ClusterModel.from_dens_and_temp(0.1, 1.0e4, cg.vikhlinin_density_profile(rho_0=1.4e5, **vd),
+                                                cg.vikhlinin_temperature_profile(T_0=10.0 / 3.0, T_min=2.0, **vt),
+                                                integrator="device")
+        ma.dm_virial, mb.dm_virial
+        ca, cb = cg.compute_centers_for_binary(np.array([7000.0] * 3), 3000.0, 500.0)
+        ics = cg.ClusterICs("c4", 2, [ma, mb], [ca, cb], [[500.0, 0.0, 0.0], [-500.0, 0.0, 0.0]],
+                            num_particles={"dm": 100_000_000, "gas": 100_000_000}, r_max=5000.0)
+        p, ms, wall = timed(lambda: ics.setup_particle_ics(prng=3), reps=2)
+        c4 = {"num_particles": {k: [int(x) for x in v] for k, v in ics.num_particles.items() if sum(v)},
+              "mass_ratio": float(ma["total_mass"].d[-1] / mb["total_mass"].d[-1]),
+              "device_ms": ms, "wall_ms": wall, "particles_per_s": 2.0e8 / (ms * 1e-3),
+              "what": "ClusterICs.setup_particle_ics, 2 halos: generate, offset, concatenate, re-sample the gas of both halos"}
+        nbytes = sum(t.numel() * t.element_size() for t in p.fields.values())
+        target = None
+        for d in ("/dev/shm", "/tmp"):
+            try:
+                if shutil.disk_usage(d).free > 2.5 * nbytes:
+                    target = d
+                    break
+            except OSError:
+                pass
+        if target is not None:
+            fn = os.path.join(target, f"cgb_bench_c4_{os.getpid()}.h5")
+            try:
+                t0 = time.perf_counter()
+                p.write_particles(fn, overwrite=True)
+                c4["hdf5_write_s"] = time.perf_counter() - t0
+                c4["hdf5_bytes"] = os.path.getsize(fn)
+                c4["hdf5_write_gbs"] = c4["hdf5_bytes"] / c4["hdf5_write_s"] / 1e9
+                c4["hdf5_where"] = target
+            finally:
+                if os.path.exists(fn):
+                    os.unlink(fn)
+        else:
+            c4["hdf5_write_s"] = None
+            c4["hdf5_note"] = "no scratch file system with room for the file"
+        out["config4_binary_merger"] = c4
+        del p
+    torch.cuda.empty_cache()
+    return out
+
+
+# --------------------------------------------------------------------------- #
 # CUDA arm
 # --------------------------------------------------------------------------- #
 def run_cuda(args):
@@ -245,6 +429,10 @@ def run_cuda(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # pinned host memory must come from the socket this GPU hangs off: bind before allocating
+    from cluster_generator_b200.hoststream import bind_host_to_gpu
+
+    cpus = bind_host_to_gpu(local) if os.environ.get("CGB_BENCH_BIND", "1") == "1" else []
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -306,6 +494,7 @@ def run_cuda(args):
         return a
 
     k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    g_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
 
     # The 16-word moment all-reduce is the path's only collective.  Default ("peer"): fused into
     # the sampler kernel -- every rank's final flush adds its partial sums to all ranks' buffers
@@ -341,6 +530,8 @@ def run_cuda(args):
         if timed_idx is not None:
             k_ev[timed_idx][1].record()
         N.check(L.cgb_sample_gas(N.ctypes.byref(g), N.ptr(g_e), N.ptr(g_rho), sp))
+        if timed_idx is not None:
+            g_ev[timed_idx].record()
         if mom_mode == "nccl":
             pending[i & 1] = dist.all_reduce(last["mom"], async_op=True)
 
@@ -373,39 +564,35 @@ def run_cuda(args):
     ms = t0.elapsed_time(t1)
     clk = clocks.stop() if rank == 0 else None
     k_ms = sum(a.elapsed_time(b) for a, b in k_ev) / args.steps
+    g_ms = sum(k[1].elapsed_time(g) for k, g in zip(k_ev, g_ev)) / args.steps
     mom = last["mom"].cpu().numpy()  # last step, summed over ranks when world > 1
-    tt = torch.tensor([ms, k_ms], dtype=f64, device=dev)
+    tt = torch.tensor([ms, k_ms, g_ms], dtype=f64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms, k_ms = float(tt[0]), float(tt[1])
+    ms, k_ms, g_ms = float(tt[0]), float(tt[1]), float(tt[2])
     ms_per_step = ms / args.steps
     value = 2.0 * n_glob / (ms_per_step * 1e-3)
     tbar = mom[1] / max(mom[0] - mom[13], 1.0)
 
-    # ---- e2e: public API with host tables in, host particles out (rank-local shard) ----
-    pin = {}
-
-    def to_host(name, t):
-        if name not in pin:
-            pin[name] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-        pin[name].copy_(t, non_blocking=True)
-        return t.numel() * t.element_size()
+    # ---- e2e: the public API with host tables in and host particles out (rank-local shard) ----
+    # generate_*_particles(host=...) generates in id-range chunks and overlaps every chunk's
+    # device->host copy with the next chunk's kernels (cluster_generator_b200/hoststream.py).
+    host_dm = host_gas = True
 
     def e2e_step(i):
+        nonlocal host_dm, host_gas
         # host -> device: the radial tables (rebuilt from the host arrays every step)
         pm.dm_virial._tables.clear()
         pm._gas_tables.clear()
         h2d = 8 * (12 * pm.num_elements + 4)  # CDF + spline-fit inputs of both species
-        p = pm.generate_dm_particles(n_glob, prng=i, shard=(rank, world), diagnostics=False)
-        q = pm.generate_gas_particles(n_glob, prng=i + 1, shard=(rank, world))
-        d2h = 0
-        for k, t in list(p.fields.items()) + list(q.fields.items()):
-            d2h += to_host(k, t.T.contiguous() if t.dim() == 2 and not t.is_contiguous() else t)
-        torch.cuda.synchronize()
-        return h2d, d2h
+        host_dm = pm.generate_dm_particles(n_glob, prng=i, shard=(rank, world), host=host_dm)
+        host_gas = pm.generate_gas_particles(n_glob, prng=i + 1, shard=(rank, world), host=host_gas)
+        # device -> host read of the step's result: the moments (mean trials) of this step
+        _ = host_dm.diagnostics["dm"].as_dict()["mean_trials"]
+        return h2d, host_dm.d2h_bytes + host_gas.d2h_bytes
 
     e2e_steps = max(2, min(args.steps, 5))
-    e2e_step(0)
+    e2e_step(0)   # allocates the pinned buffers, re-used by the timed steps
     barrier()
     w0 = time.perf_counter()
     for i in range(e2e_steps):
@@ -415,7 +602,34 @@ def run_cuda(args):
     te = torch.tensor([e2e_s], dtype=f64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = 2.0 * n_glob / float(te[0])
+    e2e_s = float(te[0])
+    e2e_value = 2.0 * n_glob / e2e_s
+
+    # the ceiling the e2e number is graded against: every rank copies the same d2h bytes from a
+    # device buffer into its pinned host buffer with plain cudaMemcpyAsync, same barrier
+    # discipline, best of 3 -- what the host can ingest from all N GPUs at once
+    src = torch.empty(d2h // 8, dtype=f64, device=dev)
+    dst = torch.empty(d2h // 8, dtype=f64, pin_memory=True)
+    ceil_s = []
+    for _ in range(4):
+        barrier()
+        w0 = time.perf_counter()
+        dst.copy_(src, non_blocking=True)
+        barrier()
+        tc = torch.tensor([time.perf_counter() - w0], dtype=f64, device=dev)
+        if world > 1:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        ceil_s.append(float(tc[0]))
+    ceil_s = min(ceil_s[1:])
+    del src, dst
+    e2e_roofline = {"bound": "pcie_d2h", "achieved": world * d2h / e2e_s / 1e9, "peak": world * d2h / ceil_s / 1e9,
+                    "unit": "GB/s", "frac": ceil_s / e2e_s,
+                    "peak_source": f"measured live: {world} ranks x {d2h / 1e9:.2f} GB pinned cudaMemcpyAsync D2H at once",
+                    "host_cpus_bound": len(cpus)}
+    del host_dm, host_gas
+
+    # ---- the other BASELINE configs at their stated sizes, device-timed ----
+    configs = run_configs(args, rank, world, dev, barrier) if os.environ.get("CGB_BENCH_CONFIGS", "1") == "1" else None
 
     if peer is not None:
         mom = mom.copy()
@@ -438,6 +652,8 @@ def run_cuda(args):
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    prof = load_ncu_profile()
+    winst = prof["warp_instructions_per_launch"] * n / prof["n_particles"] if prof else None
     flops_per_particle = F_FIXED + F_TRIAL * tbar
     k_s = k_ms * 1e-3
     ach_tflops = n * flops_per_particle / k_s / 1e12
@@ -450,7 +666,8 @@ def run_cuda(args):
         "achieved": ach_tflops, "peak": dfma.value, "unit": "TFLOP/s", "frac": ach_tflops / dfma.value,
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this
         # workload, from the ncu --set full capture summarised in profiles/r01_ncu_full_summary.md
-        "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+        "traffic": prof["dram_bytes_per_launch"] * n / prof["n_particles"] if prof else None,
+        "ncu_profile": {"file": os.path.relpath(NCU_PROFILE, ROOT), "stale": prof["stale"]} if prof else None,
         "peak_source": "DFMA microbenchmark measured live (cgb_measure_dfma_tflops); MEASURED_PEAKS.json has no FP64 figure",
         "algorithmic_flops_per_particle": flops_per_particle, "mean_trials": tbar,
         "kernel_ms": k_ms, "dm_particles_per_s_kernel": n / k_s,
@@ -461,13 +678,16 @@ def run_cuda(args):
         # what actually bounds the kernel: warp-instruction issue slots (4 schedulers per SM, one
         # warp-instruction per clock each); instruction count from the committed ncu capture,
         # duration and clock measured live
-        "issue": {"warp_instructions": NCU_WARP_INSTR_PER_LAUNCH * n / 1.0e7,
-                  "achieved": NCU_WARP_INSTR_PER_LAUNCH * n / 1.0e7 / k_s,
-                  "peak": sms.value * 4 * (clk["sm_mhz"] or 1965.0) * 1.0e6 if clk else None,
+        "issue": {"warp_instructions": winst, "achieved": winst / k_s,
+                  "peak": sms.value * 4 * (clk["sm_mhz"] or 1965.0) * 1.0e6,
                   "unit": "warp-instructions/s",
-                  "frac": (NCU_WARP_INSTR_PER_LAUNCH * n / 1.0e7 / k_s) /
-                          (sms.value * 4 * (clk["sm_mhz"] or 1965.0) * 1.0e6) if clk else None},
+                  "frac": (winst / k_s) / (sms.value * 4 * (clk["sm_mhz"] or 1965.0) * 1.0e6)} if (prof and clk) else None,
     }
+    # the gas kernel (HBM-write bound: 72 B per particle incl. the zero velocities)
+    gas_s = g_ms * 1e-3
+    roofline["gas_kernel"] = {"kernel": "cgb_gas_kernel<double,false>", "bound": "hbm", "kernel_ms": g_ms,
+                              "achieved": n * B_GAS / gas_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                              "frac": n * B_GAS / gas_s / 1e9 / hbm_peak, "particles_per_s": n / gas_s}
 
     # ---- CPU baseline (bounded sample, 1 core: the reference is single-threaded) ----
     n_cpu = 2_000_000
@@ -489,8 +709,12 @@ def run_cuda(args):
         "fE_build_ms": min(fe_ms), "fE_build_note": "bit-equal to scipy (FITPACK-exact spline fits)",
         "fE_build_fast_ms": min(fe_fast_ms), "fE_build_fast_note": "PCR spline fits, f within 1e-11 of scipy",
         "fE_build_cpu_ms": 1e3 * fe_cpu_s, "check_virial_ms": min(cv_ms),
+        "dm_particles_per_s": n_glob / (k_ms * 1e-3), "gas_particles_per_s": n_glob / (g_ms * 1e-3),
+        "value_note": "value counts DM (pos+vel) and gas (pos, zero vel) particles of one step; the DM-only rate is dm_particles_per_s",
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "what": "ClusterModel.generate_dm_particles + generate_gas_particles from host tables, all fields copied to pinned host memory"},
+                "steps": e2e_steps, "roofline": e2e_roofline,
+                "what": "ClusterModel.generate_dm_particles + generate_gas_particles(host=True) from host tables: chunked generation, every chunk's D2H copy to pinned host memory overlapped with the next chunk's kernels; gas velocities (identically zero) are host-side zeros"},
+        "configs": configs,
         # per step: cgb_sample_kernel + cgb_hard_kernel (deferred long-tail pass) + cgb_gas_kernel
         "gpu_launches": 3 * args.steps,
         "roofline": roofline,

@@ -77,6 +77,7 @@ SYMBOLS = [
     ("cgb_measure_ffma_tflops", c_int, [c_int, POINTER(c_double), c_void_p]),
     ("cgb_spline_fit_workspace_bytes", c_size_t, [c_int]),
     ("cgb_spline_fit", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    ("cgb_test_div_by_rcp", c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     ("cgb_spline_eval", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     ("cgb_eddington_workspace_bytes", c_size_t, [c_int]),
     ("cgb_eddington_df", c_int, [c_void_p, c_void_p, c_int, c_double, c_double, c_void_p, c_void_p,

@@ -675,9 +675,9 @@ static size_t edd_smem_bytes(int n)
 
 extern "C" size_t cgb_eddington_workspace_bytes(int n)
 {
-    // t_rho (n+4), c_rho (n), wrk (n), t_g (n+4), c_g (n), wrk_g (n), fit scratch 17n
+    // t_rho (n+4), c_rho (n), wrk (n), t_g (n+4), c_g (n), wrk_g (n), fit scratch 18n
     // (the three fits share one Givens factorisation of the energy grid)
-    return n > 0 ? (size_t)(23 * (size_t)n + 8) * sizeof(double) : 0;
+    return n > 0 ? (size_t)(24 * (size_t)n + 8) * sizeof(double) : 0;
 }
 
 extern "C" int cgb_eddington_df(const double* d_ee, const double* d_pden, int n, double epsabs,

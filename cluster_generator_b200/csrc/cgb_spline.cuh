@@ -2,7 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
-// d_work: n*17 doubles.  reuse_factor = 1: d_work still holds the Givens factorisation of a
+// d_work: n*18 doubles.  reuse_factor = 1: d_work still holds the Givens factorisation of a
 // previous CGB_FIT_FITPACK fit over the SAME x (only the right-hand side is processed).
 int cgb_launch_spline_fit(const double* d_x, const double* d_y, int n, double* d_t, double* d_c,
                           void* d_work, cudaStream_t s, int method, int reuse_factor);

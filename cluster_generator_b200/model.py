@@ -396,7 +396,7 @@ class ClusterModel:
         return self._gas_tables[key]
 
     def _generate_radial(self, ptype, num_particles, r_max, sub_sample, compute_potential, prng,
-                         dtype, rng, shard):
+                         dtype, rng, shard, host=False, chunk=None):
         if "gas_mass" not in self.fields:
             raise RuntimeError("This ClusterModel contains no gas!")
         num_particles, sub_sample = int(num_particles), int(sub_sample)
@@ -428,6 +428,52 @@ class ClusterModel:
             seed = PRIVATE_TRIAL_SEED
         else:
             seed = seed_from_prng(prng, 4 if tracer else 3)
+        a.d_workspace = tabs.workspace.data_ptr()
+        # tracers carry zero mass (model.py:834); gas mtot / n (model.py:917-919)
+        a.particle_mass = 0.0 if tracer else (tabs.mtot / num_particles if num_particles else 0.0)
+        a.seed = seed & 0xFFFFFFFFFFFFFFFF
+        a.out_dtype = code
+        if host and rng == "device":
+            # host-resident output: chunks staged on the device, copies overlapped with the kernels
+            from .hoststream import HostStreamer
+
+            layout = OrderedDict([("particle_position", 3)])
+            if not tracer:
+                layout["thermal_energy"] = 1
+            layout["particle_mass"] = 1
+            if not tracer:
+                layout["density"] = 1
+            if compute_potential:
+                layout["particle_potential"] = 1
+            prev = getattr(host, "_host_buffers", {}).get(ptype) if isinstance(host, ClusterParticles) else None
+            hs = HostStreamer(layout, n_loc, dtype, dev, chunk, out=prev)
+
+            def launch(stage, b0, b1):
+                a.id_begin, a.id_end, a.ld = lo + b0, lo + b1, hs.chunk
+                a.d_pos, a.d_vel, a.d_mass = stage["particle_position"].data_ptr(), None, stage["particle_mass"].data_ptr()
+                a.d_pot = stage["particle_potential"].data_ptr() if compute_potential else None
+                N.check(N.lib().cgb_sample_gas(N.ctypes.byref(a), N.ptr(stage.get("thermal_energy")),
+                                               N.ptr(stage.get("density")), N.stream_ptr()))
+
+            hb = hs.run(launch) if n_loc > 0 else hs.host
+            # the velocities are identically zero (model.py:829-831, 933-935): host-side zeros
+            velh = getattr(host, "_host_vel", {}).get(ptype) if isinstance(host, ClusterParticles) else None
+            if velh is None or velh.shape != (3, n_loc) or velh.dtype != dtype:
+                velh = torch.zeros((3, n_loc), dtype=dtype, pin_memory=True)
+            hs.copy_stream.synchronize()
+            fields = OrderedDict()
+            fields[ptype, "particle_position"] = hb.arrays["particle_position"].T
+            if not tracer:
+                fields[ptype, "thermal_energy"] = hb.arrays["thermal_energy"]
+            fields[ptype, "particle_mass"] = hb.arrays["particle_mass"]
+            if not tracer:
+                fields[ptype, "density"] = hb.arrays["density"]
+            fields[ptype, "particle_velocity"] = velh.T
+            if compute_potential:
+                fields[ptype, "particle_potential"] = hb.arrays["particle_potential"]
+            out = ClusterParticles(ptype, fields)
+            out._host_buffers, out._host_vel, out.d2h_bytes = {ptype: hb}, {ptype: velh}, hs.bytes
+            return out
         pos = torch.empty((3, n_loc), dtype=dtype, device=dev)
         vel = torch.empty((3, n_loc), dtype=dtype, device=dev)
         mass = torch.empty(n_loc, dtype=dtype, device=dev)
@@ -436,12 +482,7 @@ class ClusterModel:
         if not tracer:
             therm = torch.empty(n_loc, dtype=dtype, device=dev)
             dens = torch.empty(n_loc, dtype=dtype, device=dev)
-        a.d_workspace = tabs.workspace.data_ptr()
         a.id_begin, a.id_end, a.ld = lo, hi, n_loc
-        # tracers carry zero mass (model.py:834); gas mtot / n (model.py:917-919)
-        a.particle_mass = 0.0 if tracer else (tabs.mtot / num_particles if num_particles else 0.0)
-        a.seed = seed & 0xFFFFFFFFFFFFFFFF
-        a.out_dtype = code
         a.d_pos, a.d_vel, a.d_mass = pos.data_ptr(), vel.data_ptr(), mass.data_ptr()
         a.d_pot = pot.data_ptr() if pot is not None else None
         if n_loc > 0:
@@ -457,16 +498,23 @@ class ClusterModel:
         if compute_potential:
             fields[ptype, "particle_potential"] = pot
         del keep
+        if host:
+            from .virial import _pinned_copy
+
+            fields = OrderedDict((k, _pinned_copy(v)) for k, v in fields.items())
+            torch.cuda.current_stream().synchronize()
         return ClusterParticles(ptype, fields)
 
     def generate_gas_particles(self, num_particles, r_max=None, sub_sample=1, compute_potential=False,
-                               prng=None, *, dtype=torch.float64, rng="device", shard=None):
-        """Gas particles in hydrostatic equilibrium (model.py:838-947)."""
+                               prng=None, *, dtype=torch.float64, rng="device", shard=None, host=False,
+                               chunk=None):
+        """Gas particles in hydrostatic equilibrium (model.py:838-947).  ``host``: see
+        :meth:`VirialEquilibrium.generate_particles`."""
         return self._generate_radial("gas", num_particles, r_max, sub_sample, compute_potential, prng,
-                                     dtype, rng, shard)
+                                     dtype, rng, shard, host, chunk)
 
     def generate_tracer_particles(self, num_particles, r_max=None, sub_sample=1, prng=None, *,
-                                  dtype=torch.float64, rng="device", shard=None):
+                                  dtype=torch.float64, rng="device", shard=None, host=False, chunk=None):
         """Tracer particles following the gas distribution (model.py:766-836)."""
         return self._generate_radial("tracer", num_particles, r_max, sub_sample, False, prng, dtype,
-                                     rng, shard)
+                                     rng, shard, host, chunk)

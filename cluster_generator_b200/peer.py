@@ -11,7 +11,11 @@ rank's kernel has completed, each rank's buffer holds the global moments.
 A :class:`PeerMoments` owns an arena of ``slots`` 16-word buffers.  Calls made in the same order
 on every rank (collective semantics, like NCCL) take consecutive slots; nothing is zeroed while
 the arena is in use, so ranks may drift apart by up to ``slots`` calls without a race.  Reading a
-slot requires :meth:`fence` (local stream sync + barrier) first.
+slot requires :meth:`fence` (local stream sync + barrier) first.  A slot is never handed out
+twice: when the arena is used up :meth:`next_slot` raises, and :meth:`reset` (collective:
+fence, snapshot the diagnostics already handed out, zero the own arena, barrier) makes all
+slots available again.  Counts in a slot are exact; the floating-point sums are added with
+system-scope atomics in arrival order, so their last bits may differ from run to run.
 """
 from __future__ import annotations
 
@@ -65,13 +69,37 @@ class PeerMoments:
             self._ptrs.append(p.value)
             self._opened.append(p.value)
         self._next = 0
+        self._handed_out = []
         self._view = torch.as_tensor(_DevView(self._own, self.slots * _WORDS), device=self.device)
         dist.barrier(group=group)  # every rank has mapped every buffer before anyone writes
 
     def next_slot(self) -> int:
-        s = self._next % self.slots
+        if self._next >= self.slots:
+            raise RuntimeError(
+                f"PeerMoments arena exhausted after {self.slots} calls: call reset() on every rank "
+                f"(collective) or construct it with more slots")
+        s = self._next
         self._next += 1
         return s
+
+    def track(self, diagnostics) -> None:
+        """Remember a SamplerDiagnostics that views one of our slots, so that reset() can
+        give it a private copy before the slot is zeroed."""
+        self._handed_out.append(diagnostics)
+
+    def reset(self) -> None:
+        """Collective.  All slots become available again; diagnostics handed out so far keep
+        their values (they are detached from the arena first)."""
+        import torch.distributed as dist
+
+        self.fence()
+        for d in self._handed_out:
+            d.moments = d.moments.clone()
+        self._handed_out = []
+        self._view.zero_()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)  # nobody adds into a slot before every arena is clean
+        self._next = 0
 
     def attach(self, args: "N.SampleArgs", slot: int) -> None:
         """Point a sampler call at slot ``slot`` of every rank's arena."""

@@ -342,6 +342,8 @@ class VirialEquilibrium:
         shard=None,
         diagnostics=True,
         peer_moments=None,
+        host=False,
+        chunk=None,
     ):
         """
         Generate a set of dark matter or star particles in virial equilibrium
@@ -363,6 +365,12 @@ class VirialEquilibrium:
         peer_moments : :class:`~cluster_generator_b200.peer.PeerMoments` -- fuse the moment
             all-reduce into the kernel (sub_sample == 1): the diagnostics hold the global
             sums after ``peer_moments.fence()``, no NCCL call follows the kernel.
+        host : True, or a host-resident ClusterParticles returned by an earlier ``host=True``
+            call (its pinned buffers are re-used) -- return the fields as pinned host tensors
+            like the reference's host arrays.  The index range is generated in ``chunk``-sized
+            pieces whose device->host copies overlap the next piece's kernels
+            (:mod:`cluster_generator_b200.hoststream`); values are bit-identical to the
+            device path.
         """
         num_particles = int(num_particles)
         sub_sample = int(sub_sample)
@@ -399,10 +407,12 @@ class VirialEquilibrium:
         else:
             seed = seed_from_prng(prng, _SPECIES[self.ptype])
 
-        pos = torch.empty((3, n_loc), dtype=dtype, device=dev)
-        vel = torch.empty((3, n_loc), dtype=dtype, device=dev)
-        mass = torch.empty(n_loc, dtype=dtype, device=dev)
-        pot = torch.empty(n_loc, dtype=dtype, device=dev) if compute_potential else None
+        streamed = bool(host) and sub_sample == 1 and peer_moments is None
+        n_dev = 0 if streamed else n_loc   # host=True stages through two chunk-sized slots instead
+        pos = torch.empty((3, n_dev), dtype=dtype, device=dev)
+        vel = torch.empty((3, n_dev), dtype=dtype, device=dev)
+        mass = torch.empty(n_dev, dtype=dtype, device=dev)
+        pot = torch.empty(n_dev, dtype=dtype, device=dev) if compute_potential else None
         moments = torch.zeros(N.CGB_NMOMENTS, dtype=torch.float64, device=dev) if diagnostics else None
         peer_slot = None
         if peer_moments is not None:
@@ -435,6 +445,40 @@ class VirialEquilibrium:
                 a.hu.d_u_r = put("u_r", begin, end)
             a.hu.d_u_ct, a.hu.d_u_ph = put("u_ct", begin, end), put("u_ph", begin, end)
             a.hu.d_u_ctv, a.hu.d_u_phv = put("u_ctv", begin, end), put("u_phv", begin, end)
+
+        if host and sub_sample == 1 and peer_moments is None:
+            from .hoststream import HostStreamer
+
+            layout = OrderedDict([("particle_position", 3), ("particle_velocity", 3), ("particle_mass", 1)])
+            if compute_potential:
+                layout["particle_potential"] = 1
+            prev = getattr(host, "_host_buffers", {}).get(key) if isinstance(host, ClusterParticles) else None
+            hs = HostStreamer(layout, n_loc, dtype, dev, chunk, out=prev)
+
+            def launch(stage, b0, b1):
+                a = base_args(lo + b0, lo + b1, hs.chunk)
+                a.d_pos, a.d_vel = stage["particle_position"].data_ptr(), stage["particle_velocity"].data_ptr()
+                a.d_mass = stage["particle_mass"].data_ptr()
+                a.d_pot = stage["particle_potential"].data_ptr() if compute_potential else None
+                a.d_moments = moments.data_ptr() if moments is not None else None
+                host_u(a, lo + b0, lo + b1, True)
+                N.check(L.cgb_sample_particles(N.ctypes.byref(a), N.ptr(tabs.scratch), tabs.scratch.numel(),
+                                               N.stream_ptr()))
+
+            hb = hs.run(launch) if n_loc > 0 else hs.host
+            hs.copy_stream.synchronize()
+            fields = OrderedDict()
+            fields[key, "particle_position"] = hb.arrays["particle_position"].T
+            fields[key, "particle_velocity"] = hb.arrays["particle_velocity"].T
+            fields[key, "particle_mass"] = hb.arrays["particle_mass"]
+            if compute_potential:
+                fields[key, "particle_potential"] = hb.arrays["particle_potential"]
+            diag = {key: SamplerDiagnostics(moments, shard)} if moments is not None else {}
+            del keep
+            out = ClusterParticles(key, fields, diag)
+            out._host_buffers = {key: hb}
+            out.d2h_bytes = hs.bytes
+            return out
 
         if n_loc > 0 and sub_sample == 1:
             a = base_args(lo, hi, n_loc)
@@ -483,12 +527,28 @@ class VirialEquilibrium:
         if compute_potential:
             fields[key, "particle_potential"] = pot
         diag = {}
+        if host:
+            fields = OrderedDict((k, _pinned_copy(v)) for k, v in fields.items())
+            torch.cuda.current_stream().synchronize()
         if moments is not None:
             # sub_sample > 1: every rank draws the whole sub-sample, so its moments already are
             # the global ones (summing them over ranks would count the sub-sample world times)
             diag[key] = SamplerDiagnostics(moments, shard, reduced=peer_slot is not None or sub_sample > 1)
+            if peer_slot is not None:
+                peer_moments.track(diag[key])
         del keep
         return ClusterParticles(key, fields, diag)
+
+
+def _pinned_copy(t: torch.Tensor) -> torch.Tensor:
+    """Device field -> pinned host tensor with the same logical shape and plane-major layout."""
+    if t.dim() == 2:
+        h = torch.empty((t.shape[1], t.shape[0]), dtype=t.dtype, pin_memory=True)
+        h.copy_(t.T, non_blocking=True)
+        return h.T
+    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    h.copy_(t, non_blocking=True)
+    return h
 
 
 class SamplerDiagnostics:

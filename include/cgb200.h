@@ -84,6 +84,9 @@ int cgb_measure_ffma_tflops(int iters, double *tflops, void *stream);
 #define CGB_FIT_FITPACK 0
 #define CGB_FIT_PCR 1
 size_t cgb_spline_fit_workspace_bytes(int n);
+/* Test hook: d_q[i] = d_x[i] / d_b[i] computed the way the back-substitution divides (correctly
+ * rounded reciprocal + two FMAs); tests assert it equals the IEEE quotient bit for bit. */
+int cgb_test_div_by_rcp(const double *d_x, const double *d_b, double *d_q, int64_t n, void *stream);
 int cgb_spline_fit(const double *d_x, const double *d_y, int n, double *d_t, double *d_c,
                    void *d_work, size_t work_bytes, int method, void *stream);
 /* Evaluate the spline (nu = 0) or its first derivative (nu = 1) at m points

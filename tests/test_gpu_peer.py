@@ -77,18 +77,29 @@ pm = product_model("vikhlinin")
 peer = cg.PeerMoments(slots=4)
 n = 200_001
 out = []
-for call in range(6):                        # wraps around the 4-slot arena: sums accumulate
+for call in range(4):
+    p = pm.generate_dm_particles(n, prng=call, shard=(rank, world), peer_moments=peer)
+    out.append(p.diagnostics["dm"])
+try:                                         # a used slot is never handed out again
+    pm.generate_dm_particles(n, prng=4, shard=(rank, world), peer_moments=peer)
+    raise SystemExit("expected the exhausted arena to raise")
+except RuntimeError as e:
+    assert "exhausted" in str(e)
+peer.fence()
+assert torch.equal(out[1].moments, peer.slot(1))
+peer.reset()                                 # collective: earlier diagnostics keep their values
+for call in range(4, 6):
     p = pm.generate_dm_particles(n, prng=call % 4, shard=(rank, world), peer_moments=peer)
     out.append(p.diagnostics["dm"])
 peer.fence()
 single = pm.generate_dm_particles(n, prng=1)
 want = single.diagnostics["dm"].as_dict()
-got = out[1].all_reduce().as_dict()          # all_reduce is a no-op: already global
-scale = 2.0                                  # slot 1 holds calls 1 and 5 (same prng -> same particles)
-assert got["particles"] == scale * n and got["sum_trials"] == scale * want["sum_trials"], (got, want)
-assert got["max_trials"] == want["max_trials"]
-assert abs(got["sum_v2"] - scale * want["sum_v2"]) <= 1e-11 * got["sum_v2"]
-assert torch.equal(out[1].moments, peer.slot(1))
+for k in (1, 5):                             # calls 1 and 5 drew the same particles: per-call sums
+    got = out[k].all_reduce().as_dict()      # all_reduce is a no-op: already global
+    assert got["particles"] == n and got["sum_trials"] == want["sum_trials"], (k, got, want)
+    assert got["max_trials"] == want["max_trials"]
+    assert abs(got["sum_v2"] - want["sum_v2"]) <= 1e-11 * got["sum_v2"]
+assert torch.equal(out[5].moments, peer.slot(1))
 # virial-check histograms: integer counts, summed over ranks with the process group's all_reduce
 pv = pm.dm_virial
 mine = pm.generate_dm_particles(n, prng=1, shard=(rank, world))
@@ -117,7 +128,7 @@ print("rank", rank, "ok")
 
 def test_peer_moments_across_two_processes(tmp_path):
     """Two ranks (two GPUs when present, else both on cuda:0 with gloo for the handle exchange):
-    IPC-mapped buffers, fused reduction, slot wrap-around, close."""
+    IPC-mapped buffers, fused reduction, arena exhaustion + reset, close."""
     script = tmp_path / "worker.py"
     script.write_text(_WORKER)
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", WORLD_SIZE="2")

@@ -491,6 +491,7 @@ def run_cuda(args):
         a.particle_mass = gas_tabs.mtot / n_glob
         a.seed, a.out_dtype = seed, N.CGB_DTYPE_F64
         a.d_pos, a.d_vel, a.d_mass = g_pos.data_ptr(), g_vel.data_ptr(), g_mass.data_ptr()
+        a.flags = gas_tabs.gas_flags
         return a
 
     k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]

@@ -7,6 +7,7 @@ inverse-CDF radii, rejection-sampled speeds, behind the reference's own API
 The numerics are hand-written sm_100a CUDA reached through the C ABI in
 ``include/cgb200.h``; there is no CPU fallback.
 """
+from .codes import write_amr_particles  # noqa: F401
 from .fields import GridField  # noqa: F401
 from .ics import ClusterICs, compute_centers_for_binary  # noqa: F401
 from .model import ClusterModel  # noqa: F401

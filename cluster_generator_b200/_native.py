@@ -86,6 +86,9 @@ SYMBOLS = [
                                  c_void_p, c_void_p, c_void_p]),
     ("cgb_integrate_spline", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_double,
                                      c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
+    ("cgb_qags_replay_cache_doubles", c_size_t, [c_int]),
+    ("cgb_qags_replay", c_int, [c_void_p, c_void_p, c_int, c_double, c_double, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     ("cgb_qags_trace", c_int, [c_void_p, c_void_p, c_int, c_double, c_double, c_double, c_double,
                                c_double, c_int, c_void_p, c_void_p]),
     ("cgb_sampler_workspace_bytes", c_size_t, [POINTER(SamplerDesc)]),
@@ -98,6 +101,7 @@ SYMBOLS = [
                                         c_int, c_void_p, c_int64, c_uint64, c_int64, c_void_p,
                                         c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
     ("cgb_sample_gas", c_int, [POINTER(SampleArgs), c_void_p, c_void_p, c_void_p]),
+    ("cgb_sampler_gas_flags", c_int, [c_void_p, POINTER(c_int32), c_void_p]),
     ("cgb_screen_audit", c_int, [c_void_p, c_int64, c_int64, c_uint64, c_int64, c_void_p, c_void_p]),
     ("cgb_ppform_workspace_bytes", c_size_t, [c_int]),
     ("cgb_ppform_prepare", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
@@ -105,6 +109,8 @@ SYMBOLS = [
                               c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     ("cgb_resample_gas", c_int, [POINTER(HaloTables), c_int, c_void_p, c_int64, c_int64, c_int, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    ("cgb_resample_scalars", c_int, [POINTER(HaloTables), c_int, POINTER(c_void_p), c_int, c_void_p, c_int64,
+                                     c_int64, c_int, POINTER(c_void_p), c_int, c_void_p]),
     ("cgb_particle_histograms", c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int64, c_int, c_double,
                                         c_double, c_double, c_double, c_int, c_void_p, c_void_p]),
     ("cgb_peer_alloc", c_int, [c_size_t, POINTER(c_void_p), c_char_p]),

@@ -16,6 +16,7 @@
 #include "cgb_spline.cuh"
 
 #define QAGS_LIMIT 50
+#define QAGS_NEED_VALUES (-99)  // replay ran out of cached integrand values (CachedIntegrand)
 #define EPMACH DBL_EPSILON
 #define UFLOW DBL_MIN
 #define OFLOW DBL_MAX
@@ -48,6 +49,8 @@ struct QagsScratch {
 
 // virial.py:47  dgdp = lambda t, e: 2 * density_spline(e - t*t, 1)
 struct DgdpIntegrand {
+    __device__ __forceinline__ void advance() const {}
+    __device__ __forceinline__ bool exhausted() const { return false; }
     const double* t;   // knots of the density spline (shared memory)
     const double* wrk; // splder coefficients (shared memory)
     int nk;
@@ -60,6 +63,8 @@ struct DgdpIntegrand {
 
 // virial.py:96  rho_int = lambda e, psi: self.f(e) * np.sqrt(2 * (psi - e))
 struct RhoIntegrand {
+    __device__ __forceinline__ void advance() const {}
+    __device__ __forceinline__ bool exhausted() const { return false; }
     const double* t; // knots of f (shared memory)
     const double* c; // coefficients of f (shared memory)
     int nk;
@@ -87,6 +92,8 @@ __device__ __forceinline__ double pow15(double x)
 // model.py:219-224 / utils.py:137-142:  profile(r) = spline(r) * r**power, the integrand of
 // the potential table (power 1) and of spline-tabulated mass integrals (power 2)
 struct PowSplineIntegrand {
+    __device__ __forceinline__ void advance() const {}
+    __device__ __forceinline__ bool exhausted() const { return false; }
     const double* t;
     const double* c;
     int nk;
@@ -120,6 +127,7 @@ __device__ __forceinline__ void dqk21_warp(const F& f, double a, double b, doubl
         }
         fval = f(x);
     }
+    f.advance();  // one Gauss-Kronrod call consumed (no-op for analytic integrands)
     double fv1[10], fv2[10];
     const double fc = __shfl_sync(FULL, fval, 0);
 #pragma unroll
@@ -355,6 +363,7 @@ __device__ int dqagse_warp(const F& f, double a, double b, double epsabs, double
 
     ierro = 0;
     dqk21_warp(f, a, b, result, abserr, defabs, resabs);
+    if (f.exhausted()) { last_out = 0; return QAGS_NEED_VALUES; }
     dres = fabs(result);
     errbnd = fmax(epsabs, epsrel * dres);
     last = 1;
@@ -381,6 +390,7 @@ __device__ int dqagse_warp(const F& f, double a, double b, double epsabs, double
         erlast = errmax;
         dqk21_warp(f, a1, b1, area1, error1, resabs, defab1);
         dqk21_warp(f, a2, b2, area2, error2, resabs, defab2);
+        if (f.exhausted()) { last_out = last; return QAGS_NEED_VALUES; }
         area12 = area1 + area2; erro12 = error1 + error2;
         errsum = errsum + erro12 - errmax;
         area = area + area12 - rlist[maxerr];
@@ -592,6 +602,66 @@ cgb_integrate_spline_kernel(const double* __restrict__ t, const double* __restri
     }
 }
 
+// Integrals of HOST callables (utils.py:129-142: integrate_mass / integrate over a Python
+// profile).  The integrand cannot run on the device, the adaptive decisions can: dqagse is
+// REPLAYED against a cache of integrand values.  Gauss-Kronrod call number k of an integral
+// takes its 21 values from cache[k]; the first call(s) beyond the cache -- the whole interval,
+// later the two halves of the bisected interval -- record their abscissae instead and the
+// routine stops (QAGS_NEED_VALUES).  The host evaluates the profile on the requested abscissae
+// of ALL integrals in one vectorised call, appends the values, and launches the next replay:
+// one host call per bisection level (<= ~10) instead of one Python callback per abscissa
+// (1000 x ~86).  dqagse is deterministic, so every replay retraces the same decisions.
+struct CachedIntegrand {
+    const double* cache;  // [QAGS_MAX_CALLS][21] values, evaluation order of dqk21_warp's lanes
+    double* xreq;         // [2][21] abscissae of the next call(s)
+    int ncached;
+    mutable int k;
+    __device__ __forceinline__ double operator()(double x) const
+    {
+        const int lane = threadIdx.x & 31;
+        if (k < ncached) return cache[(size_t)k * 21 + lane];
+        if (k - ncached < 2) xreq[(k - ncached) * 21 + lane] = x;
+        return 0.0;
+    }
+    __device__ __forceinline__ void advance() const { ++k; }
+    __device__ __forceinline__ bool exhausted() const { return k > ncached; }
+};
+#define QAGS_MAX_CALLS (2 * QAGS_LIMIT - 1)
+
+// status[i]: 0 = running, 1 = done (out / last / ier written).  nreq[i]: abscissa sets requested.
+__global__ void __launch_bounds__(EDD_WARPS * 32)
+cgb_qags_replay_kernel(const double* __restrict__ a, const double* __restrict__ b, int m, double epsabs,
+                       double epsrel, const double* __restrict__ cache, const int* __restrict__ ncached,
+                       double* __restrict__ xreq, int* __restrict__ nreq, int* __restrict__ status,
+                       double* __restrict__ out, int* __restrict__ last_out, int* __restrict__ ier_out)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    QagsScratch* scr = (QagsScratch*)smem;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bin = blockIdx.x * EDD_WARPS + warp;
+    if (bin >= m || status[bin]) return;
+    CachedIntegrand f;
+    f.cache = cache + (size_t)bin * QAGS_MAX_CALLS * 21;
+    f.xreq = xreq + (size_t)bin * 42;
+    f.ncached = ncached[bin];
+    f.k = 0;
+    double result, abserr;
+    int last;
+    const int ier = dqagse_warp(f, a[bin], b[bin], epsabs, epsrel, QAGS_LIMIT, scr[warp], result, abserr, last);
+    __syncwarp();
+    if (lane == 0) {
+        if (ier == QAGS_NEED_VALUES) {
+            nreq[bin] = f.k - f.ncached;
+        } else {
+            status[bin] = 1;
+            nreq[bin] = 0;
+            out[bin] = result;
+            if (last_out) last_out[bin] = last;
+            if (ier_out) ier_out[bin] = ier;
+        }
+    }
+}
+
 // ff = g'(ee) / (sqrt(8) pi^2)                                       (virial.py:66)
 __global__ void cgb_ff_kernel(const double* __restrict__ t, const double* __restrict__ wrk, int n,
                               const double* __restrict__ ee, double inv_norm_den,
@@ -741,6 +811,27 @@ extern "C" int cgb_integrate_spline(const double* d_t, const double* d_c, int n,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cgb_integrate_spline_kernel<<<(m + EDD_WARPS - 1) / EDD_WARPS, EDD_WARPS * 32, smem, (cudaStream_t)stream>>>(
         d_t, d_c, n, d_a, d_b, m, power, epsabs, epsrel, d_out, d_last, d_ier);
+    CGB_CUDA_CHECK(cudaGetLastError());
+    return CGB_OK;
+}
+
+extern "C" size_t cgb_qags_replay_cache_doubles(int m)
+{
+    return m > 0 ? (size_t)m * QAGS_MAX_CALLS * 21 : 0;
+}
+
+extern "C" int cgb_qags_replay(const double* d_a, const double* d_b, int m, double epsabs, double epsrel,
+                               const double* d_cache, const int* d_ncached, double* d_xreq, int* d_nreq,
+                               int* d_status, double* d_out, int* d_last, int* d_ier, void* stream)
+{
+    CGB_REQUIRE(m >= 0, "cgb_qags_replay: negative count");
+    if (m == 0) return CGB_OK;
+    CGB_REQUIRE(d_a && d_b && d_cache && d_ncached && d_xreq && d_nreq && d_status && d_out,
+                "cgb_qags_replay: null pointer");
+    const size_t smem = EDD_WARPS * sizeof(QagsScratch);
+    CGB_CUDA_CHECK(cudaFuncSetAttribute(cgb_qags_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cgb_qags_replay_kernel<<<(m + EDD_WARPS - 1) / EDD_WARPS, EDD_WARPS * 32, smem, (cudaStream_t)stream>>>(
+        d_a, d_b, m, epsabs, epsrel, d_cache, d_ncached, d_xreq, d_nreq, d_status, d_out, d_last, d_ier);
     CGB_CUDA_CHECK(cudaGetLastError());
     return CGB_OK;
 }

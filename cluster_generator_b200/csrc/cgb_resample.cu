@@ -143,6 +143,97 @@ extern "C" int cgb_resample_gas(const cgb_halo_tables* halos, int num_halos, con
     return CGB_OK;
 }
 
+// Passive scalars of _sample_clusters (particles.py:606-637): for every scalar s,
+//   out_s = sum_k S_ks(r_k) rho_k(r_k) / sum_k rho_k(r_k)
+// with S_ks the cubic spline of halo k's radial profile of that scalar.  Same per-halo radii,
+// densities and mask as cgb_resample_gas; the particle's own fields are not read, so the call
+// may run before or after it.
+#define MAX_SCALARS 8
+struct ScalarParams {
+    HaloDev h[MAX_HALOS];
+    const double* sc[MAX_HALOS][MAX_SCALARS];
+    void* out[MAX_SCALARS];
+    int num_halos, num_scalars, use_radii;
+    const void* pos; long long ld; long long n;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) cgb_resample_scalars_kernel(const __grid_constant__ ScalarParams p)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const T* pos = (const T*)p.pos;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
+        const double x = (double)pos[i], y = (double)pos[p.ld + i], z = (double)pos[2 * p.ld + i];
+        double dsum = 0.0;
+        double acc[MAX_SCALARS];
+#pragma unroll
+        for (int s = 0; s < MAX_SCALARS; ++s) acc[s] = 0.0;
+        bool inside = (p.use_radii == 0);
+#pragma unroll
+        for (int k = 0; k < MAX_HALOS; ++k) {
+            if (k >= p.num_halos) break;
+            const HaloDev& h = p.h[k];
+            const double dx = __dsub_rn(x, h.cx), dy = __dsub_rn(y, h.cy), dz = __dsub_rn(z, h.cz);
+            const double r = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+            if (p.use_radii && r <= h.rcut) inside = true;
+            if (h.dens == nullptr) continue;
+            const int j = rs_find(h.dens, h.n - 3, r);
+            const double d = rs_eval(h.dens, h.n, j, r);
+            dsum = __dadd_rn(dsum, d);
+#pragma unroll
+            for (int s = 0; s < MAX_SCALARS; ++s)
+                if (s < p.num_scalars)  // s[i, j, :] = get_scalar(r[i, :]) * d[i, :]   (particles.py:621-623)
+                    acc[s] = __dadd_rn(acc[s], __dmul_rn(rs_eval(p.sc[k][s], h.n, j, r), d));
+        }
+        if (!inside) continue;
+#pragma unroll
+        for (int s = 0; s < MAX_SCALARS; ++s)
+            if (s < p.num_scalars) ((T*)p.out[s])[i] = (T)(acc[s] / dsum);
+    }
+}
+
+extern "C" int cgb_resample_scalars(const cgb_halo_tables* halos, int num_halos,
+                                    const void* const* d_scalar_pp, int num_scalars, const void* d_pos,
+                                    int64_t ld, int64_t n, int dtype, void* const* d_out, int use_radii,
+                                    void* stream)
+{
+    CGB_REQUIRE(halos != nullptr && num_halos >= 1 && num_halos <= MAX_HALOS,
+                "cgb_resample_scalars: num_halos must be 1..3, got %d", num_halos);
+    CGB_REQUIRE(num_scalars >= 1 && num_scalars <= MAX_SCALARS, "cgb_resample_scalars: 1..%d scalars, got %d",
+                MAX_SCALARS, num_scalars);
+    CGB_REQUIRE(dtype == CGB_DTYPE_F64 || dtype == CGB_DTYPE_F32, "cgb_resample_scalars: bad dtype %d", dtype);
+    CGB_REQUIRE(n >= 0 && ld >= n, "cgb_resample_scalars: bad sizes");
+    if (n == 0) return CGB_OK;
+    CGB_REQUIRE(d_pos && d_scalar_pp && d_out, "cgb_resample_scalars: null pointer");
+    ScalarParams p;
+    memset(&p, 0, sizeof(p));
+    bool any = false;
+    for (int k = 0; k < num_halos; ++k) {
+        const cgb_halo_tables& h = halos[k];
+        if (h.d_dens_pp) CGB_REQUIRE(h.n >= 4, "cgb_resample_scalars: halo %d has %d radial points", k, h.n);
+        any = any || h.d_dens_pp;
+        p.h[k].dens = h.d_dens_pp; p.h[k].n = h.n;
+        p.h[k].cx = h.center[0]; p.h[k].cy = h.center[1]; p.h[k].cz = h.center[2];
+        p.h[k].rcut = h.radius_cut;
+        for (int s = 0; s < num_scalars; ++s) {
+            p.sc[k][s] = (const double*)d_scalar_pp[k * num_scalars + s];
+            CGB_REQUIRE(!h.d_dens_pp || p.sc[k][s], "cgb_resample_scalars: halo %d lacks the table of scalar %d", k, s);
+        }
+    }
+    CGB_REQUIRE(any, "cgb_resample_scalars: no halo carries a gas profile");
+    for (int s = 0; s < num_scalars; ++s) {
+        CGB_REQUIRE(d_out[s] != nullptr, "cgb_resample_scalars: null output %d", s);
+        p.out[s] = d_out[s];
+    }
+    p.num_halos = num_halos; p.num_scalars = num_scalars; p.use_radii = use_radii;
+    p.pos = d_pos; p.ld = ld; p.n = n;
+    const unsigned blocks = (unsigned)min((long long)((n + 255) / 256), 148LL * 16);
+    if (dtype == CGB_DTYPE_F64) cgb_resample_scalars_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    else cgb_resample_scalars_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    CGB_CUDA_CHECK(cudaGetLastError());
+    return CGB_OK;
+}
+
 // ---------------------------------------------------------------------------
 // 3-D field -> particles, tri-linear  -- replaces ClusterField.map_field_to_particles
 // (fields.py:308-338), i.e. scipy.interpolate.RegularGridInterpolator(method="linear",

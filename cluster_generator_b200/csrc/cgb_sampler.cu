@@ -55,6 +55,7 @@
 #endif                     // NBUF-1 tile lifetimes before the warp has to finish it.  Measured
                            // (1e7 Vikhlinin DM): 2x128 1.06 ms, 3x96 1.13, 4x64 1.15, 4x96 1.19
 #define NBC 1024           // buckets of the CDF start-index table
+#define NBG 2048           // finer start-index table of the position-only (gas) fast path
 #ifndef LANE_CAP_PAIRS
 #define LANE_CAP_PAIRS 384 // trial pairs a particle may spend in its lane before the warp takes over (48/96/192/384: Hernquist 1.47/1.56/1.45/1.45 ms, stars 2.57/2.55/2.43/2.41)
 #endif
@@ -77,6 +78,15 @@ struct SamplerHeader {
     long long off_cdf_lut;  // unsigned[NBC]: lo | hi << 16 search range per u bucket
     long long off_cdf_iv;   // int2[n_cdf]: starting psi / f piece for CDF interval j
     long long off_aux_brk[2], off_aux_pp[2];
+    // position-only species (gas / tracer): packed tables of the fast path
+    // (one contiguous block, staged into shared memory by ONE bulk copy)
+    long long off_gas_lut;  // unsigned[NBG]: lo | hi << 16 search range per (finer) u bucket
+    long long off_gas_P;    // double[n_cdf]: copy of the CDF for the search
+    long long off_gas_A;    // double4[n_cdf]: P_j, r_j, slope_j, spline piece of CDF interval j
+    long long off_gas_B;    // double[10][n_psi - 3]: brk_lo, brk_hi, aux0[4], aux1[4]
+    long long gas_block_doubles;  // length of that block
+    int gas_fast_ok;        // set to 0 by the prepare kernels when the packing does not apply
+    int pad2;
     long long total;
     // scalars computed on the device by the prepare kernels
     double e_hi;      // upper end of the screen grid
@@ -103,6 +113,14 @@ static SamplerHeader make_layout(const cgb_sampler_desc* d)
     for (int k = 0; k < h.n_aux; ++k) {
         h.off_aux_brk[k] = take(h.n_aux_coef - 2);
         h.off_aux_pp[k] = take(4LL * (h.n_aux_coef - 3));
+    }
+    if (!h.n_f) {
+        h.off_gas_lut = take(NBG / 2);
+        h.off_gas_P = take(h.n_cdf);
+        h.off_gas_A = take(4LL * h.n_cdf);
+        h.off_gas_B = take(10LL * (h.n_psi - 3));
+        h.gas_block_doubles = o - h.off_gas_lut;
+        h.gas_fast_ok = 1;
     }
     h.total = o;
     return h;
@@ -167,9 +185,10 @@ __device__ __forceinline__ int pp_walk(const double* __restrict__ brk, int nint,
 
 // monotone bucket of a uniform in [0,1); the SAME function builds the table, so the
 // search range it yields always contains the answer
+template <int NBK = NBC>
 __device__ __forceinline__ int cdf_bucket(double u)
 {
-    return min(max(__double2int_rd(__dmul_rn(u, (double)NBC)), 0), NBC - 1);
+    return min(max(__double2int_rd(__dmul_rn(u, (double)NBK)), 0), NBK - 1);
 }
 
 // ---------------------------------------------------------------------------
@@ -177,16 +196,17 @@ __device__ __forceinline__ int cdf_bucket(double u)
 // ---------------------------------------------------------------------------
 // cdf_lut[b] = lo | hi << 16 with lo = #{j >= 1 : bucket(P[j]) < b}, hi = #{j >= 1 :
 // bucket(P[j]) <= b}: the largest j with P[j] <= u lies in [lo, hi] for bucket(u) = b.
+template <int NBK>
 __global__ void prep_cdf_lut_kernel(const double* __restrict__ P, int n, unsigned* __restrict__ lut)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= NBC) return;
+    if (b >= NBK) return;
     // P is non-decreasing: count by binary search on the bucket value
     auto count_lt = [&](int bb) {  // #{j in [1, n-1] : bucket(P[j]) < bb}
         int lo = 1, hi = n;        // first j in [1,n) with bucket(P[j]) >= bb
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
-            if (cdf_bucket(P[mid]) < bb) lo = mid + 1; else hi = mid;
+            if (cdf_bucket<NBK>(P[mid]) < bb) lo = mid + 1; else hi = mid;
         }
         return lo - 1;
     };
@@ -209,6 +229,45 @@ __global__ void prep_cdf_iv_kernel(const SamplerHeader* __restrict__ hdr, double
         jf = pp_find(base + h.off_f_brk, h.n_f - 3, psi);
     }
     ((int2*)(base + h.off_cdf_iv))[j] = make_int2(ip, jf);
+}
+
+// Packed tables of the position-only fast path.  All radial splines of a gas / tracer sampler
+// are fitted over the model's radius grid and the CDF's r-grid is that grid (plus r = 0), so a
+// CDF interval lies inside ONE spline piece and the aux / psi splines share their breakpoints:
+// record A[j] carries np.interp's (P_j, r_j, slope_j) and that piece, record B[piece] the
+// breakpoints and the coefficients of every spline -- two table reads per particle instead of
+// a dozen.  Where a caller's tables do not have that structure gas_fast_ok is cleared and the
+// kernel takes the general path.
+__global__ void prep_gas_pack_kernel(SamplerHeader* __restrict__ hdr, double* __restrict__ base)
+{
+    const SamplerHeader h = *hdr;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nint = h.n_psi - 3;
+    const double* pb = base + h.off_psi_brk;
+    bool ok = true;
+    if (h.n_aux > 0 && h.n_aux_coef != h.n_psi) ok = false;
+    if (t < h.n_cdf) {
+        const double* rc = base + h.off_cdf_r;
+        const double r0 = rc[t], r1 = (t + 1 < h.n_cdf) ? rc[t + 1] : rc[t];
+        const int pj = pp_find(pb, nint, r0);
+        if (!(pb[pj] <= r0 || pj == 0) || !(r1 <= pb[pj + 1] || pj == nint - 1)) ok = false;
+        double4 a;
+        a.x = base[h.off_cdf_P + t]; a.y = r0; a.z = base[h.off_cdf_s + t];
+        a.w = __longlong_as_double((long long)pj);
+        ((double4*)(base + h.off_gas_A))[t] = a;
+        base[h.off_gas_P + t] = a.x;
+    }
+    if (t < nint) {
+        double* B = base + h.off_gas_B + 10LL * t;
+        B[0] = pb[t]; B[1] = pb[t + 1];
+        for (int k = 0; k < 2; ++k) {
+            for (int c = 0; c < 4; ++c)
+                B[2 + 4 * k + c] = (k < h.n_aux && ok) ? base[h.off_aux_pp[k] + 4LL * t + c] : 0.0;
+            if (k < h.n_aux && ok && (base[h.off_aux_brk[k] + t] != pb[t] || base[h.off_aux_brk[k] + t + 1] != pb[t + 1]))
+                ok = false;
+        }
+    }
+    if (!ok) atomicAnd(&hdr->gas_fast_ok, 0);
 }
 
 __global__ void prep_cdf_kernel(const double* __restrict__ P, const double* __restrict__ r, int n,
@@ -448,7 +507,7 @@ __device__ __forceinline__ void load_screen(const double* base, float2* s_screen
 // largest j in [0, n_cdf-2] with P[j] <= u       (np.interp's interval, utils.py:165)
 __device__ __forceinline__ int cdf_find(const Tables& T, double u)
 {
-    const unsigned lh = __ldg(T.cdf_lut + cdf_bucket(u));
+    const unsigned lh = __ldg(T.cdf_lut + cdf_bucket<NBC>(u));
     int lo = (int)(lh & 0xffffu), hi = (int)(lh >> 16);
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
@@ -1440,6 +1499,145 @@ __global__ void __launch_bounds__(256) cgb_gas_kernel(const __grid_constant__ Sa
     }
 }
 
+// Fast path of the position-only species: one persistent 1024-thread CTA per SM with the packed
+// tables (prep_gas_pack_kernel: start-index table, CDF, record A per CDF interval, record B per
+// spline piece; 128 KB for the default 1000-point model) staged into shared memory by ONE TMA
+// bulk copy.  The kernel is a stream of random table gathers: from L1 every gather costs one
+// wavefront per distinct cache line (ncu: l1tex at 89 % of peak, the limiter of the general
+// kernel), from shared memory a handful of bank passes.  Same arithmetic as the general path.
+#define GAS_THREADS 1024
+template <typename OutT, bool HOST_U>
+__global__ void __launch_bounds__(GAS_THREADS, 1)
+cgb_gas_smem_kernel(const __grid_constant__ SampleParams p, void* aux0, void* aux1)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ unsigned long long s_mbar;
+    const SamplerHeader* hdr = (const SamplerHeader*)p.base;
+    const int npi = hdr->n_psi - 3;
+    const long long blk = hdr->gas_block_doubles;
+    {
+        const unsigned mbar_a = (unsigned)__cvta_generic_to_shared(&s_mbar);
+        const unsigned dst_a = (unsigned)__cvta_generic_to_shared(smem);
+        const unsigned bytes = (unsigned)(blk * 8);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_a) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_a), "r"(bytes) : "memory");
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_a),
+                "l"(p.base + hdr->off_gas_lut), "r"(bytes), "r"(mbar_a)
+                : "memory");
+        }
+        __syncthreads();
+        unsigned done = 0;
+        while (!done) {
+            asm volatile(
+                "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                : "=r"(done)
+                : "r"(mbar_a)
+                : "memory");
+        }
+    }
+    const double* const sm = (const double*)smem;
+    const unsigned* const lut = (const unsigned*)sm;
+    const double* const cdf_P = sm + (hdr->off_gas_P - hdr->off_gas_lut);
+    const double4* const tabA = (const double4*)(sm + (hdr->off_gas_A - hdr->off_gas_lut));
+    const double* const tabB = sm + (hdr->off_gas_B - hdr->off_gas_lut);
+    const double* const ps_brk = p.base + hdr->off_psi_brk;
+    const double* const ps_pp = p.base + hdr->off_psi_pp;
+    const long long n_local = p.id_end - p.id_begin;
+    const long long n_pairs = (n_local + 1) >> 1;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const size_t amask = 2 * sizeof(OutT) - 1;
+    const bool vec = ((p.ld & 1) == 0) && (((size_t)p.pos | (size_t)p.vel | (size_t)p.mass | (size_t)p.pot |
+                                            (size_t)aux0 | (size_t)aux1) & amask) == 0;
+    for (long long pr = (long long)blockIdx.x * blockDim.x + threadIdx.x; pr < n_pairs; pr += stride) {
+        const long long loc = 2 * pr;
+        const bool both = loc + 1 < n_local;
+        double u[2], uc[2], up[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const long long lq = both ? loc + q : loc;  // the odd tail computes particle `loc` twice
+            const unsigned long long id = (unsigned long long)(p.id_begin + lq);
+            // sub_sample: np.tile(radius_sub, s)[:n]                   (model.py:887-890)
+            const unsigned long long rid = p.radius_period > 0 ? id % (unsigned long long)p.radius_period : id;
+            if (HOST_U && p.hu.d_u_r) u[q] = p.hu.d_u_r[p.radius_period > 0 ? (long long)rid : lq];
+            else {
+                const Philox4 w = philox_rk(p.rk, (unsigned)rid, (unsigned)(rid >> 32), 0u, CGB_STREAM_RADIUS);
+                u[q] = u52(w.x, w.y);
+            }
+            if (HOST_U && p.hu.d_u_ct) { uc[q] = p.hu.d_u_ct[lq]; up[q] = p.hu.d_u_ph[lq]; }
+            else {
+                const Philox4 w = philox_rk(p.rk, (unsigned)id, (unsigned)(id >> 32), 0u, CGB_STREAM_POS_DIR);
+                uc[q] = u52(w.x, w.y); up[q] = u52(w.z, w.w);
+            }
+        }
+        // np.interp's interval: largest j with P[j] <= u                  (utils.py:165)
+        int lo[2], hi[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const unsigned lh = lut[cdf_bucket<NBG>(u[q])];
+            lo[q] = (int)(lh & 0xffffu); hi[q] = (int)(lh >> 16);
+        }
+        while (lo[0] < hi[0] || lo[1] < hi[1]) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (lo[q] < hi[q]) {
+                    const int mid = (lo[q] + hi[q] + 1) >> 1;
+                    if (cdf_P[mid] <= u[q]) lo[q] = mid; else hi[q] = mid - 1;
+                }
+            }
+        }
+        double r[2], px[2], py[2], pz[2], v0[2], v1[2], vp[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const double4 a = tabA[lo[q]];
+            r[q] = __dadd_rn(__dmul_rn(a.z, __dsub_rn(u[q], a.x)), a.y);
+            int pj = (int)__double_as_longlong(a.w);
+            const double* B = tabB + 10 * pj;
+            double2 bk = *(const double2*)B;
+            if ((r[q] >= bk.y && pj < npi - 1) || (r[q] < bk.x && pj > 0)) {
+                // r rounded onto (or past) a breakpoint: the piece FITPACK's interval search picks
+                pj = pp_walk(ps_brk, npi, pj, r[q]);
+                B = tabB + 10 * pj;
+                bk = *(const double2*)B;
+            }
+            const double dx = r[q] - bk.x;
+            if (aux0) {
+                const double2 c01 = *(const double2*)(B + 2), c23 = *(const double2*)(B + 4);
+                v0[q] = fma(fma(fma(c23.y, dx, c23.x), dx, c01.y), dx, c01.x);
+            }
+            if (aux1) {
+                const double2 c01 = *(const double2*)(B + 6), c23 = *(const double2*)(B + 8);
+                v1[q] = fma(fma(fma(c23.y, dx, c23.x), dx, c01.y), dx, c01.x);
+            }
+            if (p.pot) vp[q] = -pp_eval_at(ps_brk, ps_pp, pj, r[q]);  // same breakpoints (checked by the prepare kernel)
+            const double ct = __dadd_rn(-1.0, __dmul_rn(2.0, uc[q]));
+            const double st = sqrt(__dmul_rn(__dsub_rn(1.0, ct), __dadd_rn(1.0, ct)));
+            double sp, cp;
+            sincos2pi(up[q], &sp, &cp);
+            const double rs = __dmul_rn(r[q], st);
+            px[q] = __dmul_rn(rs, cp); py[q] = __dmul_rn(rs, sp); pz[q] = __dmul_rn(r[q], ct);
+        }
+        store_pair<OutT>(p.pos, loc, px[0], px[1], both, vec);
+        store_pair<OutT>(p.pos, p.ld + loc, py[0], py[1], both, vec);
+        store_pair<OutT>(p.pos, 2 * p.ld + loc, pz[0], pz[1], both, vec);
+        if (p.vel) {
+            store_pair<OutT>(p.vel, loc, 0.0, 0.0, both, vec);
+            store_pair<OutT>(p.vel, p.ld + loc, 0.0, 0.0, both, vec);
+            store_pair<OutT>(p.vel, 2 * p.ld + loc, 0.0, 0.0, both, vec);
+        }
+        if (p.mass) store_pair<OutT>(p.mass, loc, p.particle_mass, p.particle_mass, both, vec);
+        if (aux0) store_pair<OutT>(aux0, loc, v0[0], v0[1], both, vec);
+        if (aux1) store_pair<OutT>(aux1, loc, v1[0], v1[1], both, vec);
+        if (p.pot) store_pair<OutT>(p.pot, loc, vp[0], vp[1], both, vec);
+        if (p.radius) {
+            p.radius[loc] = r[0];
+            if (both) p.radius[loc + 1] = r[1];
+        }
+    }
+}
+
 template <typename OutT, bool HOST_U>
 __global__ void __launch_bounds__(256)
 cgb_assemble_kernel(SampleParams p, const double* __restrict__ r_sub, const double* __restrict__ v_sub,
@@ -1489,7 +1687,9 @@ cgb_assemble_kernel(SampleParams p, const double* __restrict__ r_sub, const doub
 static int check_desc(const cgb_sampler_desc* d, const char* who)
 {
     CGB_REQUIRE(d != nullptr, "%s: null descriptor", who);
-    CGB_REQUIRE(d->n_cdf >= 2 && d->n_cdf < 65535 && d->d_cdf_P && d->d_cdf_r, "%s: CDF table needs >= 2 entries", who);
+    CGB_REQUIRE(d->n_cdf >= 2 && d->d_cdf_P && d->d_cdf_r, "%s: CDF table needs >= 2 entries", who);
+    // the start-index tables pack two 16-bit interval numbers per bucket
+    CGB_REQUIRE(d->n_cdf < 65535, "%s: n_cdf must be < 65535 (got %d)", who, d->n_cdf);
     CGB_REQUIRE(d->n_psi >= 4 && d->d_psi_t && d->d_psi_c, "%s: psi spline needs >= 4 coefficients", who);
     CGB_REQUIRE((d->d_f_t == nullptr) == (d->d_f_c == nullptr), "%s: f knots/coeffs must both be given", who);
     if (d->d_f_t) CGB_REQUIRE(d->n_f >= 4, "%s: f spline needs >= 4 coefficients", who);
@@ -1524,7 +1724,7 @@ extern "C" int cgb_sampler_prepare(const cgb_sampler_desc* desc, void* d_workspa
     prep_cdf_kernel<<<(h.n_cdf + 255) / 256, 256, 0, s>>>(desc->d_cdf_P, desc->d_cdf_r, h.n_cdf,
                                                          base + h.off_cdf_P, base + h.off_cdf_r,
                                                          base + h.off_cdf_s);
-    prep_cdf_lut_kernel<<<NBC / 256, 256, 0, s>>>(desc->d_cdf_P, h.n_cdf, (unsigned*)(base + h.off_cdf_lut));
+    prep_cdf_lut_kernel<NBC><<<NBC / 256, 256, 0, s>>>(desc->d_cdf_P, h.n_cdf, (unsigned*)(base + h.off_cdf_lut));
     if ((rc = cgb_launch_pp_convert(desc->d_psi_t, desc->d_psi_c, h.n_psi, base + h.off_psi_brk,
                                     base + h.off_psi_pp, s))) return rc;
     for (int k = 0; k < h.n_aux; ++k)
@@ -1537,6 +1737,11 @@ extern "C" int cgb_sampler_prepare(const cgb_sampler_desc* desc, void* d_workspa
         prep_screen_kernel<<<NB / 256, 256, 0, s>>>((const SamplerHeader*)base, base);
     }
     prep_cdf_iv_kernel<<<(h.n_cdf + 255) / 256, 256, 0, s>>>((const SamplerHeader*)base, base);
+    if (!h.n_f) {
+        prep_cdf_lut_kernel<NBG><<<NBG / 256, 256, 0, s>>>(desc->d_cdf_P, h.n_cdf, (unsigned*)(base + h.off_gas_lut));
+        const int nt = max(h.n_cdf, h.n_psi - 3);
+        prep_gas_pack_kernel<<<(nt + 255) / 256, 256, 0, s>>>((SamplerHeader*)base, base);
+    }
     CGB_CUDA_CHECK(cudaGetLastError());
     return CGB_OK;
 }
@@ -1588,6 +1793,23 @@ static int fill_params(const cgb_sample_args* a, SampleParams& sp, const char* w
 static bool any_host_u(const cgb_host_uniforms& hu)
 {
     return hu.d_u_r || hu.d_u_ct || hu.d_u_ctv || hu.d_u_trial;
+}
+
+// flags word for cgb_sample_gas: CGB_SAMPLE_GAS_PACKED | (packed-block bytes / 256) << 8 when the
+// prepared workspace carries valid packed tables, else 0.  Synchronises `stream` (one 4-byte and
+// one 8-byte read-back; call it once per prepared workspace).
+extern "C" int cgb_sampler_gas_flags(const void* d_workspace, int32_t* flags_out, void* stream)
+{
+    CGB_REQUIRE(d_workspace && flags_out, "cgb_sampler_gas_flags: null pointer");
+    SamplerHeader h;
+    CGB_CUDA_CHECK(cudaMemcpyAsync(&h, d_workspace, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CGB_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    *flags_out = 0;
+    if (!h.n_f && h.gas_fast_ok && h.gas_block_doubles > 0) {
+        const long long units = (h.gas_block_doubles * 8 + 255) / 256;
+        if (units < (1 << 22)) *flags_out = CGB_SAMPLE_GAS_PACKED | (int32_t)(units << 8);
+    }
+    return CGB_OK;
 }
 
 extern "C" size_t cgb_sample_scratch_bytes(void)
@@ -1647,8 +1869,28 @@ extern "C" int cgb_sample_gas(const cgb_sample_args* args, void* d_aux_out0, voi
     const long long n_local = sp.id_end - sp.id_begin;
     if (n_local == 0) return CGB_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    const unsigned blocks = (unsigned)min(((n_local + 1) / 2 + 255) / 256, 148LL * 16);
     const bool f32 = args->out_dtype == CGB_DTYPE_F32, hu = any_host_u(args->hu);
+    // fast path: packed tables in shared memory.  The table size is a function of the sizes in
+    // the header, which the caller's descriptor fixed; whether the packing applies is known on
+    // the device only (gas_fast_ok), so that flag travels with args->flags once the caller has
+    // read it back -- the wrappers do so when the tables are prepared.
+    if ((args->flags & CGB_SAMPLE_GAS_PACKED) && n_local >= 4096) {
+        int dev = 0, sms = 0;
+        CGB_CUDA_CHECK(cudaGetDevice(&dev));
+        CGB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const size_t smem = (size_t)(args->flags >> 8) * 256;  // packed-block size in 256-byte units
+        if (smem > 0 && smem <= 220 * 1024) {
+#define CGB_LAUNCH_GAS_SMEM(T, H) do { \
+            CGB_CUDA_CHECK(cudaFuncSetAttribute(cgb_gas_smem_kernel<T, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            cgb_gas_smem_kernel<T, H><<<sms, GAS_THREADS, smem, s>>>(sp, d_aux_out0, d_aux_out1); } while (0)
+            if (f32) { if (hu) CGB_LAUNCH_GAS_SMEM(float, true); else CGB_LAUNCH_GAS_SMEM(float, false); }
+            else { if (hu) CGB_LAUNCH_GAS_SMEM(double, true); else CGB_LAUNCH_GAS_SMEM(double, false); }
+#undef CGB_LAUNCH_GAS_SMEM
+            CGB_CUDA_CHECK(cudaGetLastError());
+            return CGB_OK;
+        }
+    }
+    const unsigned blocks = (unsigned)min(((n_local + 1) / 2 + 255) / 256, 148LL * 16);
     if (f32) {
         if (hu) cgb_gas_kernel<float, true><<<blocks, 256, 0, s>>>(sp, d_aux_out0, d_aux_out1);
         else cgb_gas_kernel<float, false><<<blocks, 256, 0, s>>>(sp, d_aux_out0, d_aux_out1);

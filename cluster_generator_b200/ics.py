@@ -145,14 +145,14 @@ class ClusterICs:
     def resample_particle_ics(self, parts, passive_scalars=None):
         """Re-sample density, thermal energy and velocity of relaxed gas particles / cells from
         the initial hydrostatic profiles (ics.py:377-422)."""
-        if passive_scalars:
-            raise NotImplementedError("passive scalars are outside the particle-sampling path")
         m, c, v = self.models, self.center, self.velocity
         if self.num_halos == 1:
             return resample_one_cluster(parts, m[0], c[0], v[0])
         if self.num_halos == 2:
-            return resample_two_clusters(parts, m[0], m[1], c[0], c[1], v[0], v[1], self.r_max)
-        return resample_three_clusters(parts, m[0], m[1], m[2], c[0], c[1], c[2], v[0], v[1], v[2], self.r_max)
+            return resample_two_clusters(parts, m[0], m[1], c[0], c[1], v[0], v[1], self.r_max,
+                                         passive_scalars=passive_scalars)
+        return resample_three_clusters(parts, m[0], m[1], m[2], c[0], c[1], c[2], v[0], v[1], v[2], self.r_max,
+                                       passive_scalars=passive_scalars)
 
     # -- parameter files (ics.py:202-320; same keys, written with PyYAML instead of ruamel) -----
     def to_file(self, filename, overwrite=False):

@@ -23,7 +23,7 @@ from scipy.interpolate import InterpolatedUnivariateSpline
 
 from . import _native as N
 from .particles import ClusterParticles
-from .utils import _MH_G, _MSUN_G, G, kpc_to_cm, integrate, integrate_mass, keV, mp, mu, mue, mylog, parse_prng, seed_from_prng, unit_array
+from .utils import _MH_G, _MSUN_G, G, kpc_to_cm, integrate, integrate_device, integrate_mass, integrate_mass_device, keV, mp, mu, mue, mylog, parse_prng, seed_from_prng, unit_array
 from .virial import (PRIVATE_TRIAL_SEED, DeviceSpline, SamplerDiagnostics, SamplerTables,  # noqa: F401
                      VirialEquilibrium, _out_code, radius_cdf_table, shard_bounds)
 
@@ -189,7 +189,9 @@ class ClusterModel:
     @classmethod
     def _from_scratch(cls, fields, stellar_density=None, integrator="host"):
         """model.py:213-269.  ``integrator="device"`` runs the N potential integrals
-        (utils.py:137-142, ~1 s of host ``quad`` calls) on the GPU instead."""
+        (utils.py:137-142) and the mass integrals of the constructors (utils.py:129-134) -- ~1-3 s
+        of host ``quad`` callbacks -- through the device QUADPACK restatement instead
+        (utils.integrate_spline_device / quad_callable_device)."""
         if integrator not in ("host", "device"):
             raise ValueError("integrator must be 'host' or 'device'")
         rr = np.asarray(fields["radius"])
@@ -215,7 +217,7 @@ class ClusterModel:
         if stellar_density is not None:
             fields["stellar_density"] = stellar_density(rr)
             mylog.info("Integrating stellar mass profile.")
-            fields["stellar_mass"] = integrate_mass(stellar_density, rr)
+            fields["stellar_mass"] = (integrate_mass_device if integrator == "device" else integrate_mass)(stellar_density, rr)
 
         mdm = np.array(fields["total_mass"], dtype=np.float64)
         ddm = np.array(fields["total_density"], dtype=np.float64)
@@ -249,7 +251,7 @@ class ClusterModel:
         fields["radius"] = rr
         fields["total_density"] = total_density(rr)
         mylog.info("Integrating total mass profile.")
-        fields["total_mass"] = integrate_mass(total_density, rr)
+        fields["total_mass"] = (integrate_mass_device if integrator == "device" else integrate_mass)(total_density, rr)
         fields["gravitational_field"] = -G * fields["total_mass"] / (fields["radius"] ** 2)
         return cls._from_scratch(fields, stellar_density=stellar_density, integrator=integrator)
 
@@ -269,7 +271,7 @@ class ClusterModel:
         pressure_spline = InterpolatedUnivariateSpline(rr, fields["pressure"])
         dPdr = pressure_spline(rr, 1)
         fields["gravitational_field"] = dPdr / fields["density"]
-        fields["gas_mass"] = integrate_mass(density, rr)
+        fields["gas_mass"] = (integrate_mass_device if integrator == "device" else integrate_mass)(density, rr)
         fields["total_mass"] = -fields["radius"] ** 2 * fields["gravitational_field"] / G
         total_mass_spline = InterpolatedUnivariateSpline(rr, fields["total_mass"])
         dMdr = total_mass_spline(rr, nu=1)
@@ -290,26 +292,31 @@ class ClusterModel:
                                       num_points=num_points, integrator=integrator)
 
     @classmethod
-    def from_dens_and_tden(cls, rmin, rmax, density, total_density, stellar_density=None, num_points=1000):
+    def from_dens_and_tden(cls, rmin, rmax, density, total_density, stellar_density=None, num_points=1000,
+                           integrator="host"):
         """Hydrostatic model from gas density and total density (model.py:565-618)."""
+        if integrator not in ("host", "device"):
+            raise ValueError("integrator must be 'host' or 'device'")
+        imass = integrate_mass_device if integrator == "device" else integrate_mass
+        iint = integrate_device if integrator == "device" else integrate
         mylog.info("Computing the profiles from density and total density.")
         rr = np.logspace(np.log10(rmin), np.log10(rmax), num_points, endpoint=True)
         fields = OrderedDict()
         fields["radius"] = rr
         fields["density"] = density(rr)
         fields["total_density"] = total_density(rr)
-        fields["total_mass"] = integrate_mass(total_density, rr)
-        fields["gas_mass"] = integrate_mass(density, rr)
+        fields["total_mass"] = imass(total_density, rr)
+        fields["gas_mass"] = imass(density, rr)
         fields["gravitational_field"] = -G * fields["total_mass"] / (fields["radius"] ** 2)
         g = fields["gravitational_field"]
         g_r = InterpolatedUnivariateSpline(rr, g)
         dPdr_int = lambda r: density(r) * g_r(r)
-        P = -integrate(dPdr_int, rr)
+        P = -iint(dPdr_int, rr)
         dPdr_int2 = lambda r: density(r) * g[-1] * (rr[-1] / r) ** 2
         P -= quad(dPdr_int2, rr[-1], np.inf, limit=100)[0]
         fields["pressure"] = P
         fields["temperature"] = fields["pressure"] * mu * mp / fields["density"] / keV
-        return cls._from_scratch(fields, stellar_density=stellar_density)
+        return cls._from_scratch(fields, stellar_density=stellar_density, integrator=integrator)
 
     def set_rmax(self, r_max):
         """Truncate the model at ``r_max`` (model.py:271-293; the reference passes kwargs its
@@ -433,6 +440,7 @@ class ClusterModel:
         a.particle_mass = 0.0 if tracer else (tabs.mtot / num_particles if num_particles else 0.0)
         a.seed = seed & 0xFFFFFFFFFFFFFFFF
         a.out_dtype = code
+        a.flags = tabs.gas_flags
         if host and rng == "device":
             # host-resident output: chunks staged on the device, copies overlapped with the kernels
             from .hoststream import HostStreamer

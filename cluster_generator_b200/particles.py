@@ -551,8 +551,7 @@ def _sample_clusters(particles, hses, center, velocity, radii=None, resample=Fal
     from . import _native as N
     from .virial import DeviceSpline
 
-    if passive_scalars:
-        raise NotImplementedError("passive scalars are outside the particle-sampling path")
+    passive_scalars = list(passive_scalars) if passive_scalars else []
     num_halos = len(hses)
     if not 1 <= num_halos <= 3:
         raise ValueError("between one and three halos are supported")
@@ -588,6 +587,29 @@ def _sample_clusters(particles, hses, center, velocity, radii=None, resample=Fal
             N.check(L.cgb_ppform_prepare(N.ptr(s.t), N.ptr(s.c), s.n, N.ptr(ws), nb, N.stream_ptr()))
             keep.append((s, ws))
             setattr(halos[i], name, ws.data_ptr())
+    if passive_scalars:
+        # particles.py:606-637: mass-weighted scalar profiles, into the particles' own scalar fields
+        ns = len(passive_scalars)
+        tabs = (N.ctypes.c_void_p * (num_halos * ns))()
+        outs = (N.ctypes.c_void_p * ns)()
+        for i, hse in enumerate(hses):
+            if "density" not in hse:
+                continue
+            rr = np.asarray(hse["radius"], dtype=np.float64)
+            for j, name in enumerate(passive_scalars):
+                sp = DeviceSpline.fit(rr, np.asarray(hse[name], dtype=np.float64))
+                nb = L.cgb_ppform_workspace_bytes(sp.n)
+                ws = N.workspace(nb)
+                N.check(L.cgb_ppform_prepare(N.ptr(sp.t), N.ptr(sp.c), sp.n, N.ptr(ws), nb, N.stream_ptr()))
+                keep.append((sp, ws))
+                tabs[i * ns + j] = ws.data_ptr()
+        for j, name in enumerate(passive_scalars):
+            t = particles["gas", name]
+            if t.dtype != dtype or not t.is_contiguous() or t.numel() != n:
+                raise ValueError(f"passive scalar {name!r} must be a contiguous (n,) field of the gas dtype")
+            outs[j] = t.data_ptr()
+        N.check(L.cgb_resample_scalars(halos, num_halos, tabs, ns, N.ptr(pos), n, n, code, outs,
+                                       1 if radii is not None else 0, N.stream_ptr()))
     N.check(L.cgb_resample_gas(halos, num_halos, N.ptr(pos), n, n, code, N.ptr(dens), N.ptr(therm),
                                N.ptr(vel), N.ptr(mass) if resample else None,
                                1 if radii is not None else 0, N.stream_ptr()))
@@ -632,14 +654,16 @@ def resample_one_cluster(particles, hse, center, velocity):
     return _sample_clusters(particles, [hse], [center], [velocity], resample=True)
 
 
-def resample_two_clusters(particles, hse1, hse2, center1, center2, velocity1, velocity2, radii):
+def resample_two_clusters(particles, hse1, hse2, center1, center2, velocity1, velocity2, radii,
+                          passive_scalars=None):
     """particles.py:747-768"""
     return _sample_clusters(particles, [hse1, hse2], [center1, center2], [velocity1, velocity2],
-                            radii=radii, resample=True)
+                            radii=radii, resample=True, passive_scalars=passive_scalars)
 
 
 def resample_three_clusters(particles, hse1, hse2, hse3, center1, center2, center3, velocity1,
-                            velocity2, velocity3, radii):
+                            velocity2, velocity3, radii, passive_scalars=None):
     """particles.py:771-795"""
     return _sample_clusters(particles, [hse1, hse2, hse3], [center1, center2, center3],
-                            [velocity1, velocity2, velocity3], radii=radii, resample=True)
+                            [velocity1, velocity2, velocity3], radii=radii, resample=True,
+                            passive_scalars=passive_scalars)

@@ -139,3 +139,78 @@ def integrate_spline_device(spline, a, b, power=1, epsabs=1.49e-8, epsrel=1.49e-
     N.check(N.lib().cgb_integrate_spline(N.ptr(td), N.ptr(cd), n, N.ptr(ad), N.ptr(bd), a.size, int(power),
                                          epsabs, epsrel, N.ptr(out), None, None, N.stream_ptr()))
     return out.cpu().numpy().reshape(a.shape)
+
+
+def quad_callable_device(fn, a, b, epsabs=1.49e-8, epsrel=1.49e-8, return_info=False):
+    """``[quad(fn, a_i, b_i)[0] for i]`` for a vectorised HOST callable ``fn`` with QUADPACK's
+    adaptive decisions on the GPU (``cgb_qags_replay``).
+
+    ``scipy.integrate.quad`` calls ``fn`` once per abscissa -- ~86 000 Python callbacks for the
+    1000 integrals of ``integrate_mass``.  Here ``dqagse`` is replayed on the device against a
+    cache of integrand values; after every replay the abscissae all unfinished integrals need
+    next (the two halves of their worst interval) come back in ONE array, ``fn`` is evaluated on
+    it in one vectorised call and the values are appended to the cache: one host call per
+    bisection level.  The decisions are QUADPACK's (the same restatement that builds f(E)); the
+    integrand values are ``fn``'s own, evaluated on arrays instead of Python scalars -- identical
+    wherever NumPy's array arithmetic equals its scalar arithmetic (everything but ``**`` with
+    non-integer exponents on some CPUs), so tables agree with ``quad`` to the last bit or two.
+    """
+    import torch
+
+    from . import _native as N
+
+    a = np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), np.shape(b) or np.shape(a)))
+    b = np.ascontiguousarray(np.broadcast_to(np.asarray(b, dtype=np.float64), a.shape))
+    shape, m = a.shape, a.size
+    if m == 0:
+        return np.zeros(shape)
+    L = N.lib()
+    dev = N.require_cuda()
+    ad, bd = N.dev_f64(a.ravel(), dev), N.dev_f64(b.ravel(), dev)
+    ncalls = int(L.cgb_qags_replay_cache_doubles(m)) // (21 * m)
+    cache = torch.empty((m, ncalls, 21), dtype=torch.float64, device=dev)
+    ncached = torch.zeros(m, dtype=torch.int32, device=dev)
+    status = torch.zeros(m, dtype=torch.int32, device=dev)
+    nreq = torch.zeros(m, dtype=torch.int32, device=dev)
+    xreq = torch.empty((m, 2, 21), dtype=torch.float64, device=dev)
+    out = torch.empty(m, dtype=torch.float64, device=dev)
+    last = torch.zeros(m, dtype=torch.int32, device=dev)
+    ier = torch.zeros(m, dtype=torch.int32, device=dev)
+    have = np.zeros(m, dtype=np.int64)
+    levels = 0
+    for levels in range(1, 2 * 50 + 2):
+        N.check(L.cgb_qags_replay(N.ptr(ad), N.ptr(bd), m, epsabs, epsrel, N.ptr(cache), N.ptr(ncached),
+                                  N.ptr(xreq), N.ptr(nreq), N.ptr(status), N.ptr(out), N.ptr(last), N.ptr(ier),
+                                  N.stream_ptr()))
+        nr = nreq.cpu().numpy().astype(np.int64)
+        idx = np.nonzero(nr)[0]
+        if idx.size == 0:
+            break
+        x = xreq.cpu().numpy()
+        # requested call sets, integral-major: rows (i, j) for j < nr[i]
+        rows = np.repeat(idx, nr[idx])
+        cols = np.concatenate([np.arange(k) for k in nr[idx]])
+        vals = np.asarray(fn(x[rows, cols].ravel()), dtype=np.float64).reshape(-1, 21)
+        rows_d = torch.as_tensor(rows, device=dev)
+        kpos_d = torch.as_tensor(have[rows] + cols, device=dev)
+        cache[rows_d, kpos_d] = torch.as_tensor(vals, device=dev)
+        have[idx] += nr[idx]
+        ncached.copy_(torch.as_tensor(have, dtype=torch.int32))
+    else:
+        raise RuntimeError("cgb_qags_replay did not converge")
+    res = out.cpu().numpy().reshape(shape)
+    if return_info:
+        return res, dict(last=last.cpu().numpy().reshape(shape), ier=ier.cpu().numpy().reshape(shape), levels=levels)
+    return res
+
+
+def integrate_mass_device(profile, rr):
+    """``integrate_mass`` (utils.py:129-134) through :func:`quad_callable_device`."""
+    rr = np.asarray(rr, dtype=np.float64)
+    return 4.0 * np.pi * quad_callable_device(lambda r: profile(r) * r * r, np.zeros_like(rr), rr)
+
+
+def integrate_device(profile, rr):
+    """``integrate`` (utils.py:137-142) through :func:`quad_callable_device`."""
+    rr = np.asarray(rr, dtype=np.float64)
+    return quad_callable_device(profile, rr, np.full_like(rr, rr[-1]))

@@ -117,6 +117,12 @@ class SamplerTables:
         self.workspace = N.workspace(nb, dev)
         N.check(N.lib().cgb_sampler_prepare(N.ctypes.byref(d), N.ptr(self.workspace), nb, N.stream_ptr()))
         self.scratch = N.workspace(N.lib().cgb_sample_scratch_bytes(), dev)
+        #: cgb_sample_args.flags for cgb_sample_gas (packed shared-memory tables), read back once
+        self.gas_flags = 0
+        if f_spline is None:
+            fl = N.ctypes.c_int32(0)
+            N.check(N.lib().cgb_sampler_gas_flags(N.ptr(self.workspace), N.ctypes.byref(fl), N.stream_ptr()))
+            self.gas_flags = int(fl.value)
 
 
 def radius_cdf_table(r, m, r_max=None):

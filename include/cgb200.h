@@ -133,6 +133,20 @@ int cgb_integrate_spline(const double *d_t, const double *d_c, int n, const doub
                          const double *d_b, int m, int power, double epsabs, double epsrel,
                          double *d_out, int *d_last, int *d_ier, void *stream);
 
+/* T (tables): quad(profile, a_i, b_i) for a HOST callable -- integrate_mass / integrate
+ * (utils.py:129-142) without one Python callback per abscissa.  QUADPACK's dqagse is replayed on
+ * the device against a cache of integrand values: replay number r consumes d_cache[i][k][21]
+ * for the d_ncached[i] Gauss-Kronrod calls evaluated so far and, for every integral that needs
+ * more, writes the 21 abscissae of its next one or two calls to d_xreq[i][2][21] and their
+ * number to d_nreq[i]; the caller evaluates the profile on all of them at once (vectorised),
+ * appends the values to the cache in the same order, bumps d_ncached and calls again until
+ * every d_status[i] is 1 (d_out / d_last / d_ier written then).  Caller zeroes d_status and
+ * d_ncached before the first call; d_cache holds cgb_qags_replay_cache_doubles(m) doubles. */
+size_t cgb_qags_replay_cache_doubles(int m);
+int cgb_qags_replay(const double *d_a, const double *d_b, int m, double epsabs, double epsrel,
+                    const double *d_cache, const int *d_ncached, double *d_xreq, int *d_nreq,
+                    int *d_status, double *d_out, int *d_last, int *d_ier, void *stream);
+
 /* Diagnostic: ONE QAGS integral with its full adaptive state, so tests can compare
  * the device quadrature decision for decision with QUADPACK (scipy's
  * quad(..., full_output=1): last, alist, blist, rlist, elist).
@@ -202,7 +216,7 @@ typedef struct cgb_sample_args {
     double particle_mass;    /* mtot / num_particles (virial.py:225-227) */
     uint64_t seed;
     int32_t out_dtype;       /* CGB_DTYPE_F64 / CGB_DTYPE_F32 for pos/vel/mass/pot */
-    int32_t flags;           /* reserved, 0 */
+    int32_t flags;           /* 0, or the value cgb_sampler_gas_flags returned (cgb_sample_gas only) */
     /* outputs, local index = id - id_begin; pos/vel are (3, ld) plane-major ("SoA":
        the memory layout of unyt_array([x,y,z]).T, virial.py:180-187,216-223) */
     void *d_pos;
@@ -281,6 +295,15 @@ int cgb_generate_velocities(const double *d_psi, const double *d_vesc, const dou
  * (d_vel == NULL: the caller owns zeroed storage).  Two particles per thread, 16-byte stores.
  * d_aux_out[k]: nullable f64/f32 arrays (out_dtype) for aux spline k. */
 int cgb_sample_gas(const cgb_sample_args *args, void *d_aux_out0, void *d_aux_out1, void *stream);
+/* Fast path of cgb_sample_gas.  cgb_sampler_prepare packs the tables of a position-only sampler
+ * (d_f_t == NULL) for shared-memory residence when every radial spline shares the radius grid of
+ * the CDF, as ClusterModel's tables do (model.py:879-941).  Whether that applied is known on the
+ * device; cgb_sampler_gas_flags reads it back ONCE per prepared workspace (it synchronises the
+ * stream) and returns the value to put into cgb_sample_args.flags for cgb_sample_gas: with it the
+ * call launches one persistent CTA per SM with the tables staged by a TMA bulk copy, without it
+ * (flags = 0) the general kernel.  Results are identical either way. */
+#define CGB_SAMPLE_GAS_PACKED 1
+int cgb_sampler_gas_flags(const void *d_workspace, int32_t *flags_out, void *stream);
 
 /* ------------------------------------------------------------------------ */
 /* Multi-halo gas re-sampling ("next" row 1 of SURVEY.md section 8(f))        */
@@ -309,6 +332,15 @@ typedef struct cgb_halo_tables {
 int cgb_resample_gas(const cgb_halo_tables *halos, int num_halos, const void *d_pos, int64_t ld,
                      int64_t n, int dtype, void *d_density, void *d_thermal, void *d_vel,
                      void *d_mass, int use_radii, void *stream);
+
+/* Passive scalars of _sample_clusters (particles.py:606-637, 745-795): out_s = sum_k S_ks(r_k)
+ * rho_k(r_k) / sum_k rho_k(r_k).  halos as for cgb_resample_gas (only d_dens_pp, n, center and
+ * radius_cut are read); d_scalar_pp: HOST array [num_halos * num_scalars] of ppform tables
+ * (cgb_ppform_prepare) of IUS(radius, scalar), halo-major, NULL for halos without gas;
+ * d_out: HOST array of num_scalars (1..8) device arrays (n,), updated where the mask allows. */
+int cgb_resample_scalars(const cgb_halo_tables *halos, int num_halos, const void *const *d_scalar_pp,
+                         int num_scalars, const void *d_pos, int64_t ld, int64_t n, int dtype,
+                         void *const *d_out, int use_radii, void *stream);
 
 /* Virial-check histograms (north_star item 4): counts of r (log-spaced
  * bins on [r_lo, r_hi)), |v| (linear on [0, v_max)) and E = psi(r) - v^2/2 (linear on

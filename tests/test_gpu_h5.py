@@ -148,3 +148,31 @@ def test_ics_particle_files(tmp_path):
     assert torch.isfinite(again2["gas", "thermal_energy"]).all()
     inside = ((first["gas", "particle_position"] - torch.as_tensor(c1, device="cuda")).norm(dim=1) < 5000.0)
     torch.testing.assert_close(again2["gas", "density"][inside], dens0[inside], rtol=1e-12, atol=0.0)
+
+
+def test_write_amr_particles(tmp_path):
+    """codes.py:16-73: the flat GAMER / FLASH / RAMSES particle file, hdf5 and fortran formats."""
+    from scipy.io import FortranFile
+
+    P, _ = _particles(n=50_000)
+    ptype_num = {"dm": 2, "gas": 1}
+    fn = cg.write_amr_particles(P, tmp_path / "amr.h5", ["dm", "gas"], ptype_num)
+    root = H.load(fn)
+    assert sorted(root["children"]) == ["particle_mass", "particle_position", "particle_type", "particle_velocity"]
+    for f in ("particle_position", "particle_velocity", "particle_mass"):
+        want = np.concatenate([_np(P["dm", f]), _np(P["gas", f])], axis=0)
+        np.testing.assert_array_equal(root["children"][f]["data"], want)
+    np.testing.assert_array_equal(root["children"]["particle_type"]["data"],
+                                  np.concatenate([2.0 * np.ones(50_000), np.ones(50_000)]))
+    with pytest.raises(IOError):
+        cg.write_amr_particles(P, fn, ["dm"], ptype_num, overwrite=False)
+    # cgs output scales by the kpc / Msun / Myr definitions of utils.py
+    fn2 = cg.write_amr_particles(P, tmp_path / "amr_cgs.h5", ["dm"], ptype_num, in_cgs=True)
+    pos = H.load(fn2)["children"]["particle_position"]["data"]
+    np.testing.assert_allclose(pos, _np(P["dm", "particle_position"]) * 3.0856775809623245e21, rtol=1e-15)
+    fn3 = cg.write_amr_particles(P, tmp_path / "amr.dat", ["dm", "gas"], ptype_num, format="fortran")
+    with FortranFile(fn3, "r") as f:
+        assert int(f.read_ints(np.int32)[0]) == 100_000
+        rec = f.read_reals(np.float64).reshape(100_000, 7)
+    np.testing.assert_array_equal(rec[:50_000, :3], _np(P["dm", "particle_position"]))
+    np.testing.assert_array_equal(rec[50_000:, 6], _np(P["gas", "particle_mass"]))

@@ -27,6 +27,11 @@ from .utils import _MH_G, _MSUN_G, G, kpc_to_cm, integrate, integrate_device, in
 from .virial import (PRIVATE_TRIAL_SEED, DeviceSpline, SamplerDiagnostics, SamplerTables,  # noqa: F401
                      VirialEquilibrium, _out_code, radius_cdf_table, shard_bounds)
 
+#: default of the constructors' ``integrator`` argument: "host" = the reference's own scipy
+#: ``quad`` loops (tables bit-equal to the reference, 1-3 s), "device" = the same QUADPACK
+#: decisions on the GPU (tables equal to ~1e-13, 4-11 ms)
+DEFAULT_INTEGRATOR = "host"
+
 _UNITS = {
     "radius": "kpc", "density": "Msun/kpc**3", "total_density": "Msun/kpc**3",
     "dark_matter_density": "Msun/kpc**3", "stellar_density": "Msun/kpc**3",
@@ -187,11 +192,12 @@ class ClusterModel:
         return cls(np.asarray(fields["radius"]).size, OrderedDict(fields))
 
     @classmethod
-    def _from_scratch(cls, fields, stellar_density=None, integrator="host"):
+    def _from_scratch(cls, fields, stellar_density=None, integrator=None):
         """model.py:213-269.  ``integrator="device"`` runs the N potential integrals
         (utils.py:137-142) and the mass integrals of the constructors (utils.py:129-134) -- ~1-3 s
         of host ``quad`` callbacks -- through the device QUADPACK restatement instead
         (utils.integrate_spline_device / quad_callable_device)."""
+        integrator = DEFAULT_INTEGRATOR if integrator is None else integrator
         if integrator not in ("host", "device"):
             raise ValueError("integrator must be 'host' or 'device'")
         rr = np.asarray(fields["radius"])
@@ -244,20 +250,21 @@ class ClusterModel:
         return cls(rr.size, fields)
 
     @classmethod
-    def no_gas(cls, rmin, rmax, total_density, stellar_density=None, num_points=1000, integrator="host"):
+    def no_gas(cls, rmin, rmax, total_density, stellar_density=None, num_points=1000, integrator=None):
         """Model without a gas component (model.py:620-656)."""
         rr = np.logspace(np.log10(rmin), np.log10(rmax), num_points, endpoint=True)
         fields = OrderedDict()
         fields["radius"] = rr
         fields["total_density"] = total_density(rr)
         mylog.info("Integrating total mass profile.")
+        integrator = DEFAULT_INTEGRATOR if integrator is None else integrator
         fields["total_mass"] = (integrate_mass_device if integrator == "device" else integrate_mass)(total_density, rr)
         fields["gravitational_field"] = -G * fields["total_mass"] / (fields["radius"] ** 2)
         return cls._from_scratch(fields, stellar_density=stellar_density, integrator=integrator)
 
     @classmethod
     def from_dens_and_temp(cls, rmin, rmax, density, temperature, stellar_density=None, num_points=1000,
-                           integrator="host"):
+                           integrator=None):
         """Hydrostatic model from gas density and temperature (model.py:474-523)."""
         mylog.info("Computing the profiles from density and temperature.")
         rr = np.logspace(np.log10(rmin), np.log10(rmax), num_points, endpoint=True)
@@ -271,6 +278,7 @@ class ClusterModel:
         pressure_spline = InterpolatedUnivariateSpline(rr, fields["pressure"])
         dPdr = pressure_spline(rr, 1)
         fields["gravitational_field"] = dPdr / fields["density"]
+        integrator = DEFAULT_INTEGRATOR if integrator is None else integrator
         fields["gas_mass"] = (integrate_mass_device if integrator == "device" else integrate_mass)(density, rr)
         fields["total_mass"] = -fields["radius"] ** 2 * fields["gravitational_field"] / G
         total_mass_spline = InterpolatedUnivariateSpline(rr, fields["total_mass"])
@@ -280,7 +288,7 @@ class ClusterModel:
 
     @classmethod
     def from_dens_and_entr(cls, rmin, rmax, density, entropy, stellar_density=None, num_points=1000,
-                           integrator="host"):
+                           integrator=None):
         """Hydrostatic model from gas density and entropy profiles (model.py:525-563):
         kT = S n_e^(2/3) with n_e = rho / (mue mp) in cm^-3 (entropy in keV cm^2)."""
         from .radial_profiles import RadialProfile
@@ -293,8 +301,9 @@ class ClusterModel:
 
     @classmethod
     def from_dens_and_tden(cls, rmin, rmax, density, total_density, stellar_density=None, num_points=1000,
-                           integrator="host"):
+                           integrator=None):
         """Hydrostatic model from gas density and total density (model.py:565-618)."""
+        integrator = DEFAULT_INTEGRATOR if integrator is None else integrator
         if integrator not in ("host", "device"):
             raise ValueError("integrator must be 'host' or 'device'")
         imass = integrate_mass_device if integrator == "device" else integrate_mass

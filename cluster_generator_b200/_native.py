@@ -26,6 +26,7 @@ CGB_DTYPE_F64 = 0
 CGB_DTYPE_F32 = 1
 CGB_NMOMENTS = 16
 CGB_FIT_FITPACK, CGB_FIT_PCR = 0, 1
+CGB_FIT_REUSE_FACTOR = 0x100
 MOMENT_NAMES = (
     "particles", "sum_trials", "max_trials", "sum_v2", "sum_psi", "sum_x", "sum_y", "sum_z",
     "sum_vx", "sum_vy", "sum_vz", "nonpositive_envelopes", "cooperative_finishes", "failures",
@@ -77,6 +78,7 @@ SYMBOLS = [
     ("cgb_measure_ffma_tflops", c_int, [c_int, POINTER(c_double), c_void_p]),
     ("cgb_spline_fit_workspace_bytes", c_size_t, [c_int]),
     ("cgb_spline_fit", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    ("cgb_test_givens_cycles", c_int, [c_void_p]),
     ("cgb_test_div_by_rcp", c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     ("cgb_spline_eval", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     ("cgb_eddington_workspace_bytes", c_size_t, [c_int]),

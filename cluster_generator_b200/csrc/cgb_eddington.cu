@@ -756,8 +756,14 @@ extern "C" int cgb_eddington_df(const double* d_ee, const double* d_pden, int n,
                                 size_t work_bytes, int fit_method, void* stream)
 {
     CGB_REQUIRE(n >= 8, "cgb_eddington_df: need at least 8 radial points, got %d", n);
+    // CGB_FIT_REUSE_FACTOR: d_work still holds the Givens factorisation of this d_ee from an
+    // earlier CGB_FIT_FITPACK call (the other species of the same model share the energy grid)
+    const int reuse_first = (fit_method & CGB_FIT_REUSE_FACTOR) ? 1 : 0;
+    fit_method &= ~CGB_FIT_REUSE_FACTOR;
     CGB_REQUIRE(fit_method == CGB_FIT_FITPACK || fit_method == CGB_FIT_PCR,
                 "cgb_eddington_df: unknown fit method %d", fit_method);
+    CGB_REQUIRE(!reuse_first || fit_method == CGB_FIT_FITPACK,
+                "cgb_eddington_df: CGB_FIT_REUSE_FACTOR needs CGB_FIT_FITPACK");
     CGB_REQUIRE(d_ee && d_pden && d_g && d_ff && d_f_t && d_f_c && d_work,
                 "cgb_eddington_df: null pointer");
     if (work_bytes < cgb_eddington_workspace_bytes(n)) {
@@ -766,17 +772,18 @@ extern "C" int cgb_eddington_df(const double* d_ee, const double* d_pden, int n,
         return CGB_E_WORKSPACE;
     }
     cudaStream_t s = (cudaStream_t)stream;
+    // the fit scratch (Givens factorisation, re-usable) comes first, then the per-call arrays
     double* w = (double*)d_work;
+    void* fit_scratch = w;          w += 18 * (size_t)n;
     double* t_rho = w;              w += n + 4;
     double* c_rho = w;              w += n;
     double* wrk = w;                w += n;
     double* t_g = w;                w += n + 4;
     double* c_g = w;                w += n;
     double* wrk_g = w;              w += n;
-    void* fit_scratch = w;
     int rc;
     // density_spline = IUS(ee, pden)                                  (virial.py:45)
-    if ((rc = cgb_launch_spline_fit(d_ee, d_pden, n, t_rho, c_rho, fit_scratch, s, fit_method, 0))) return rc;
+    if ((rc = cgb_launch_spline_fit(d_ee, d_pden, n, t_rho, c_rho, fit_scratch, s, fit_method, reuse_first))) return rc;
     if ((rc = cgb_launch_splder_coeffs(t_rho, c_rho, n, wrk, s))) return rc;
     const size_t smem = edd_smem_bytes(n);
     CGB_REQUIRE(smem <= 227 * 1024, "cgb_eddington_df: n = %d needs %zu B of shared memory", n, smem);

@@ -176,8 +176,7 @@ class VirialEquilibrium:
         self.model = model
         self._tables = {}
         self._psi_pp = None
-        self.g = None
-        self.qags_last = self.qags_ier = None
+        self._g_dev = self._last_dev = self._ier_dev = None
         if df is None:
             self._generate_df()
         else:
@@ -201,15 +200,43 @@ class VirialEquilibrium:
         last = torch.empty(n, dtype=torch.int32, device=dev)
         ier = torch.empty(n, dtype=torch.int32, device=dev)
         nb = L.cgb_eddington_workspace_bytes(n)
-        work = N.workspace(nb, dev)
+        method = N.CGB_FIT_FITPACK if FE_SPLINE_FIT == "fitpack" else N.CGB_FIT_PCR
+        # the species of one model share the energy grid: the workspace -- with the Givens
+        # factorisation of that grid inside -- is kept on the model and re-used
+        cache = getattr(self.model, "_fe_fit_cache", None)
+        key = (n, ee.tobytes(), str(dev))
+        if method == N.CGB_FIT_FITPACK and cache is not None and cache[0] == key:
+            work = cache[1]
+            method |= N.CGB_FIT_REUSE_FACTOR
+        else:
+            work = N.workspace(nb, dev)
         N.check(L.cgb_eddington_df(N.ptr(ee_d), N.ptr(pd_d), n, 1.49e-05, 1.49e-05, N.ptr(g), N.ptr(ff),
                                    N.ptr(ft), N.ptr(fc), N.ptr(last), N.ptr(ier), N.ptr(work), nb,
-                                   N.CGB_FIT_FITPACK if FE_SPLINE_FIT == "fitpack" else N.CGB_FIT_PCR,
-                                   N.stream_ptr()))
+                                   method, N.stream_ptr()))
+        if (method & ~N.CGB_FIT_REUSE_FACTOR) == N.CGB_FIT_FITPACK:
+            try:
+                self.model._fe_fit_cache = (key, work)
+            except AttributeError:
+                pass
         self.f = DeviceSpline(ft, fc)
-        self.g = g.cpu().numpy()
-        self.qags_last, self.qags_ier = last.cpu().numpy(), ier.cpu().numpy()
+        # g and QUADPACK's per-bin diagnostics stay on the device until somebody asks for them
+        self._g_dev, self._last_dev, self._ier_dev = g, last, ier
         self.df = unit_array(ff.cpu().numpy()[::-1].copy(), "Msun*Myr**3/kpc**6")
+
+    @property
+    def g(self):
+        """g(E_i) = int_0^sqrt(E_i) 2 rho'(E_i - t^2) dt, the N quadratures of virial.py:54-63."""
+        return None if self._g_dev is None else self._g_dev.cpu().numpy()
+
+    @property
+    def qags_last(self):
+        """QUADPACK's number of sub-intervals per energy bin."""
+        return None if self._last_dev is None else self._last_dev.cpu().numpy()
+
+    @property
+    def qags_ier(self):
+        """QUADPACK's error flag per energy bin."""
+        return None if self._ier_dev is None else self._ier_dev.cpu().numpy()
 
     @property
     def ee(self):

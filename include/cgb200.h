@@ -83,9 +83,17 @@ int cgb_measure_ffma_tflops(int iters, double *tflops, void *stream);
  * reduction of the same collocation system, ~20 us, coefficients within 1e-13 of FITPACK's. */
 #define CGB_FIT_FITPACK 0
 #define CGB_FIT_PCR 1
+/* cgb_eddington_df only, OR-ed onto CGB_FIT_FITPACK: d_work was used by an earlier
+ * CGB_FIT_FITPACK call with the SAME d_ee values and has not been written since -- its Givens
+ * factorisation of the energy grid is re-used (the dark-matter and stellar f(E) of one model
+ * share the grid, model.py:111-127), all three fits only rotate their right-hand side. */
+#define CGB_FIT_REUSE_FACTOR 0x100
 size_t cgb_spline_fit_workspace_bytes(int n);
 /* Test hook: d_q[i] = d_x[i] / d_b[i] computed the way the back-substitution divides (correctly
  * rounded reciprocal + two FMAs); tests assert it equals the IEEE quotient bit for bit. */
+/* Test / profiling hook: clock64 ticks of the four phases (serial prologue, pipelined run, serial
+ * epilogue, back-substitution) of the last FITPACK-exact fit: [0..3] factorising, [4..7] re-using. */
+int cgb_test_givens_cycles(long long *host8);
 int cgb_test_div_by_rcp(const double *d_x, const double *d_b, double *d_q, int64_t n, void *stream);
 int cgb_spline_fit(const double *d_x, const double *d_y, int n, double *d_t, double *d_c,
                    void *d_work, size_t work_bytes, int method, void *stream);

@@ -22,7 +22,11 @@ def timed(fn, reps=5):
 
 
 v = pm.dm_virial
-print("f(E) build exact ms", timed(lambda: v._generate_df()))
+def fresh():
+    pm._fe_fit_cache = None
+    v._generate_df()
+print("f(E) build exact, fresh ms", timed(fresh))
+print("f(E) build exact, shared grid ms", timed(lambda: v._generate_df()))
 print("check_virial ms", timed(lambda: v.check_virial(), 2))
 if "gas_mass" in pm.fields:
     pm.generate_gas_particles(n, prng=1)

@@ -550,3 +550,40 @@ def test_gadget_multi_file_layout(tmp_path):
     assert A.num_particles == S.num_particles
     for k in S.fields:
         assert torch.equal(A[k], S[k]), k
+
+
+def test_h5py_opens_the_written_files(tmp_path):
+    """Interchange with the real libhdf5: runs wherever h5py is installed -- it is not
+    in the build image, where this test skips and ``oracle/h5_oracle.py`` (pinned by a file libhdf5
+    wrote) stands in.  Datasets, shapes, dtypes, string and array attributes must come back."""
+    h5py = pytest.importorskip("h5py")
+    if getattr(h5py, "__cgb_test_stub__", False):
+        pytest.skip("only the in-memory stand-in of tests/_refshim is importable")
+    p = str(tmp_path / "x.h5")
+    a = np.arange(12, dtype=np.float64).reshape(4, 3)
+    b = np.arange(5, dtype=np.float32)
+    with H5Writer(p) as w:
+        w.create_group("/dm")
+        w.write("/dm/particle_position", a)
+        w.write("/dm/particle_mass", b)
+        w.set_attr("/dm/particle_position", "units", "kpc")
+        w.create_group("/Header")
+        w.set_attr("/Header", "NumPart_ThisFile", np.array([0, 4, 0, 0, 0, 0], dtype=np.uint32))
+        w.set_attr("/Header", "Time", 0.0)
+    with h5py.File(p, "r") as f:
+        assert sorted(f.keys()) == ["Header", "dm"]
+        np.testing.assert_array_equal(f["dm/particle_position"][:], a)
+        np.testing.assert_array_equal(f["dm/particle_mass"][:], b)
+        u = f["dm/particle_position"].attrs["units"]
+        assert (u.decode() if isinstance(u, bytes) else u) == "kpc"
+        np.testing.assert_array_equal(f["Header"].attrs["NumPart_ThisFile"], [0, 4, 0, 0, 0, 0])
+        assert f["Header"].attrs["Time"] == 0.0
+    # and the other direction: a file h5py wrote, read by the native reader
+    q = str(tmp_path / "y.h5")
+    with h5py.File(q, "w") as f:
+        g = f.create_group("gas")
+        d = g.create_dataset("density", data=b.astype(np.float64))
+        d.attrs["units"] = "Msun/kpc**3"
+    with H5Reader(q) as r:
+        np.testing.assert_array_equal(r.read("/gas/density"), b.astype(np.float64))
+        assert r.attrs("/gas/density")["units"] == "Msun/kpc**3"

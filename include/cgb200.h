@@ -78,7 +78,8 @@ int cgb_measure_ffma_tflops(int iters, double *tflops, void *stream);
  * not inspect the data: x must be strictly increasing (scipy raises ValueError for that at
  * virial.py:45); the Python wrapper checks it on the host, where the tables come from.
  * method: CGB_FIT_FITPACK = fpcurf's own Givens-rotation solve, coefficients bit-equal to
- * scipy's (serial recurrence, ~0.3 ms for n = 1000; used by the f(E) build, whose quadrature
+ * scipy's (a serial dependency chain run by one thread from registers, ~0.6 ms for n = 1000,
+ * ~0.13 ms when the factorisation is re-used; used by the f(E) build, whose quadrature
  * decisions and spline derivative amplify coefficient noise); CGB_FIT_PCR = parallel cyclic
  * reduction of the same collocation system, ~20 us, coefficients within 1e-13 of FITPACK's. */
 #define CGB_FIT_FITPACK 0
@@ -89,14 +90,14 @@ int cgb_measure_ffma_tflops(int iters, double *tflops, void *stream);
  * share the grid, model.py:111-127), all three fits only rotate their right-hand side. */
 #define CGB_FIT_REUSE_FACTOR 0x100
 size_t cgb_spline_fit_workspace_bytes(int n);
-/* Test hook: d_q[i] = d_x[i] / d_b[i] computed the way the back-substitution divides (correctly
- * rounded reciprocal + two FMAs); tests assert it equals the IEEE quotient bit for bit. */
-/* Test / profiling hook: clock64 ticks of the four phases (serial prologue, pipelined run, serial
- * epilogue, back-substitution) of the last FITPACK-exact fit: [0..3] factorising, [4..7] re-using. */
-int cgb_test_givens_cycles(long long *host8);
-int cgb_test_div_by_rcp(const double *d_x, const double *d_b, double *d_q, int64_t n, void *stream);
 int cgb_spline_fit(const double *d_x, const double *d_y, int n, double *d_t, double *d_c,
                    void *d_work, size_t work_bytes, int method, void *stream);
+/* Test hook: d_q[i] = d_x[i] / d_b[i] computed the way the back-substitution divides (correctly
+ * rounded reciprocal + two FMAs); tests assert it equals the IEEE quotient bit for bit. */
+int cgb_test_div_by_rcp(const double *d_x, const double *d_b, double *d_q, int64_t n, void *stream);
+/* Profiling hook: clock64 ticks of the four phases (serial prologue, register-window run, serial
+ * epilogue, back-substitution) of the last FITPACK-exact fit: [0..3] factorising, [4..7] re-using. */
+int cgb_test_givens_cycles(long long *host8);
 /* Evaluate the spline (nu = 0) or its first derivative (nu = 1) at m points
  * (FITPACK splev/splder arithmetic, extrapolating outside the knots). */
 int cgb_spline_eval(const double *d_t, const double *d_c, int n, const double *d_x, double *d_y,
@@ -113,7 +114,7 @@ int cgb_spline_eval(const double *d_t, const double *d_c, int n, const double *d
  * The quadrature is a decision-for-decision restatement of QUADPACK dqagse
  * (21-point Gauss-Kronrod, bisection, epsilon extrapolation, limit = 50).
  * fit_method: CGB_FIT_FITPACK makes g, ff and the f spline bit-equal to scipy's (the three
- * spline fits use fpcurf's own solve, ~1.2 ms each); CGB_FIT_PCR is ~10x faster overall and
+ * spline fits share one factorisation by fpcurf's own solve, ~1.1 ms in all); CGB_FIT_PCR is ~3.5x faster overall and
  * within 1e-11 of it. */
 size_t cgb_eddington_workspace_bytes(int n);
 int cgb_eddington_df(const double *d_ee, const double *d_pden, int n, double epsabs, double epsrel,

@@ -783,8 +783,7 @@ extern "C" int cgb_eddington_df(const double* d_ee, const double* d_pden, int n,
     double* wrk_g = w;              w += n;
     int rc;
     // density_spline = IUS(ee, pden)                                  (virial.py:45)
-    if ((rc = cgb_launch_spline_fit(d_ee, d_pden, n, t_rho, c_rho, fit_scratch, s, fit_method, reuse_first))) return rc;
-    if ((rc = cgb_launch_splder_coeffs(t_rho, c_rho, n, wrk, s))) return rc;
+    if ((rc = cgb_launch_spline_fit(d_ee, d_pden, n, t_rho, c_rho, fit_scratch, s, fit_method, reuse_first, wrk))) return rc;
     const size_t smem = edd_smem_bytes(n);
     CGB_REQUIRE(smem <= 227 * 1024, "cgb_eddington_df: n = %d needs %zu B of shared memory", n, smem);
     CGB_CUDA_CHECK(cudaFuncSetAttribute(cgb_eddington_g_kernel,
@@ -793,13 +792,12 @@ extern "C" int cgb_eddington_df(const double* d_ee, const double* d_pden, int n,
         d_ee, n, t_rho, wrk, epsabs, epsrel, d_g, d_last, d_ier);
     CGB_CUDA_CHECK(cudaGetLastError());
     // g_spline = IUS(ee, g); ff = g_spline(ee, 1) / (sqrt(8) pi^2)    (virial.py:65-66)
-    if ((rc = cgb_launch_spline_fit(d_ee, d_g, n, t_g, c_g, fit_scratch, s, fit_method, fit_method == CGB_FIT_FITPACK))) return rc;
-    if ((rc = cgb_launch_splder_coeffs(t_g, c_g, n, wrk_g, s))) return rc;
+    if ((rc = cgb_launch_spline_fit(d_ee, d_g, n, t_g, c_g, fit_scratch, s, fit_method, fit_method == CGB_FIT_FITPACK, wrk_g))) return rc;
     const double den = sqrt(8.0) * (M_PI * M_PI);
     cgb_ff_kernel<<<(n + 255) / 256, 256, 0, s>>>(t_g, wrk_g, n, d_ee, den, d_ff);
     CGB_CUDA_CHECK(cudaGetLastError());
     // self.f = IUS(ee, ff)                                            (virial.py:67)
-    if ((rc = cgb_launch_spline_fit(d_ee, d_ff, n, d_f_t, d_f_c, fit_scratch, s, fit_method, fit_method == CGB_FIT_FITPACK))) return rc;
+    if ((rc = cgb_launch_spline_fit(d_ee, d_ff, n, d_f_t, d_f_c, fit_scratch, s, fit_method, fit_method == CGB_FIT_FITPACK, nullptr))) return rc;
     return CGB_OK;
 }
 

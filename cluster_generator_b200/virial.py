@@ -192,13 +192,12 @@ class VirialEquilibrium:
             raise ValueError("x must be strictly increasing")
         dev = N.require_cuda()
         L = N.lib()
-        ee_d, pd_d = N.dev_f64(ee, dev), N.dev_f64(pden, dev)
-        g = torch.empty(n, dtype=torch.float64, device=dev)
-        ff = torch.empty(n, dtype=torch.float64, device=dev)
-        ft = torch.empty(n + 4, dtype=torch.float64, device=dev)
-        fc = torch.empty(n, dtype=torch.float64, device=dev)
-        last = torch.empty(n, dtype=torch.int32, device=dev)
-        ier = torch.empty(n, dtype=torch.int32, device=dev)
+        both = N.dev_f64(np.stack([ee, pden]), dev)       # one host -> device copy
+        ee_d, pd_d = both[0], both[1]
+        out = torch.empty(4 * n + 4, dtype=torch.float64, device=dev)
+        g, ff, fc, ft = out[:n], out[n:2 * n], out[2 * n:3 * n], out[3 * n:]
+        flags = torch.empty(2 * n, dtype=torch.int32, device=dev)
+        last, ier = flags[:n], flags[n:]
         nb = L.cgb_eddington_workspace_bytes(n)
         method = N.CGB_FIT_FITPACK if FE_SPLINE_FIT == "fitpack" else N.CGB_FIT_PCR
         # the species of one model share the energy grid: the workspace -- with the Givens

@@ -12,4 +12,4 @@ v._generate_df()
 torch.cuda.synchronize()
 buf = (ctypes.c_longlong * 8)()
 N.lib().cgb_test_givens_cycles(buf)
-print("givens cycles factor [prologue, run, epilogue, fpback]", list(buf[:4]), "apply", list(buf[4:]))
+print("givens cycles factor [prologue, run, epilogue, fpback]", list(buf[:4]), "apply", list(buf[4:8]))

@@ -26,7 +26,7 @@ PRIVATE_TRIAL_SEED = 0xC6A4A7935BD1E995
 _SPECIES = {"dark_matter": 1, "stellar": 2, "gas": 3, "tracer": 4}
 
 #: Spline solver of the f(E) build: "fitpack" (default) reproduces scipy's numbers to the
-#: bit (fpcurf's Givens solve, ~1.1 ms per f(E)); "pcr" is ~3.5x faster and within 1e-11.
+#: bit (fpcurf's Givens solve, ~0.85 ms per f(E)); "pcr" is ~2.6x faster and within 1e-11.
 FE_SPLINE_FIT = "fitpack"
 
 

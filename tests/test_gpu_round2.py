@@ -502,3 +502,53 @@ def test_cold_model_build_on_the_device_matches_the_host_tables(name):
         np.testing.assert_allclose(np.asarray(dm[k]), np.asarray(pm[k]), rtol=1e-11, atol=1e-300, err_msg=k)
     np.testing.assert_allclose(dm.dm_virial.df.d, pm.dm_virial.df.d, rtol=1e-8)
     assert dt < 1.0
+
+
+# --------------------------------------------------------------------------- #
+# edge cases of the round-2 paths: empty and tiny inputs, tables too large for shared memory
+# --------------------------------------------------------------------------- #
+def test_round2_paths_edge_cases(oracle):
+    import cluster_generator_b200 as cg
+    from cluster_generator_b200 import _native as N
+    from cluster_generator_b200.utils import quad_callable_device
+
+    pm = product_model("vikhlinin")
+    # host streaming with nothing, one particle, fewer particles than a chunk
+    for n in (0, 1, 3, 4097):
+        with _seeded(5):
+            h = pm.generate_gas_particles(n, prng=0, host=True)
+            d = pm.generate_gas_particles(n, prng=0)
+            hd = pm.generate_dm_particles(n, prng=0, host=True, compute_potential=True)
+            dd = pm.generate_dm_particles(n, prng=0, compute_potential=True)
+        for a, b in ((h, d), (hd, dd)):
+            assert a.num_particles == b.num_particles
+            for k in b.fields:
+                assert a[k].shape == b[k].shape and torch.equal(a[k], b[k].cpu()), (n, k)
+    # the screen audit of nothing
+    assert pm.dm_virial.screen_audit(0)["trials"] == 0
+    # quad of host callables: no integrals, one integral, a zero-width interval
+    assert quad_callable_device(np.sin, np.zeros(0), np.zeros(0)).shape == (0,)
+    one = quad_callable_device(np.sin, np.array([0.0]), np.array([np.pi]))
+    np.testing.assert_allclose(one, [2.0], rtol=1e-14)
+    assert quad_callable_device(np.sin, np.array([1.5]), np.array([1.5]))[0] == 0.0
+    # a radial grid whose packed gas tables exceed the shared-memory budget: the general kernel
+    # runs (flags without the size fit), same numbers as a direct evaluation of the splines
+    dens = cg.vikhlinin_density_profile(4.2e5, 100.0, 1000.0, 1.0, 0.67, 3.0)
+    temp = cg.vikhlinin_temperature_profile(10.0, 0.0, 2.0, 1.0, 1500.0, 6.0, 80.0, 1.0)
+    big = cg.ClusterModel.from_dens_and_temp(0.1, 1.0e4, dens, temp, num_points=2600, integrator="device")
+    tabs = big._gas_sampler_tables(None, False)
+    assert tabs.gas_flags & 1 and (tabs.gas_flags >> 8) * 256 > 220 * 1024
+    with _seeded(9):
+        g = big.generate_gas_particles(50_001, prng=0)
+    r = torch.linalg.norm(g["gas", "particle_position"], dim=1).cpu().numpy()
+    from scipy.interpolate import InterpolatedUnivariateSpline as IUS
+    want = IUS(big["radius"].d, big["density"].d)(r)
+    np.testing.assert_allclose(_np(g["gas", "density"]), want, rtol=1e-9)
+    assert r.max() <= 1.0e4 * (1 + 1e-12) and np.isfinite(_np(g["gas", "thermal_energy"])).all()
+    # the start-index tables pack 16-bit interval numbers: clear message beyond that
+    d = N.SamplerDesc()
+    d.n_cdf, d.n_psi = 70_000, 8
+    dummy = torch.zeros(16, dtype=torch.float64, device="cuda")
+    d.d_cdf_P = d.d_cdf_r = d.d_psi_t = d.d_psi_c = dummy.data_ptr()
+    assert N.lib().cgb_sampler_workspace_bytes(N.ctypes.byref(d)) == 0
+    assert b"n_cdf must be < 65535" in N.lib().cgb_last_error()

@@ -44,6 +44,9 @@
 #ifndef LEAN_SCREEN_ALL
 #define LEAN_SCREEN_ALL 1  // screen all 2*LEAN_PAIRS trials before looking at any result
 #endif
+#ifndef PH0_Q
+#define PH0_Q 2            // particles per lane whose phase-0 table walks are interleaved
+#endif
 #ifndef WARPS
 #define WARPS 16           // warps per CTA
 #endif
@@ -56,6 +59,8 @@
                            // (1e7 Vikhlinin DM): 2x128 1.06 ms, 3x96 1.13, 4x64 1.15, 4x96 1.19
 #define NBC 1024           // buckets of the CDF start-index table
 #define NBG 2048           // finer start-index table of the position-only (gas) fast path
+#define GAS_A_STRIDE 6      // doubles per record A: 48 B = 3 x 16 B, so consecutive records rotate through
+                           // all eight 16-byte bank groups (a 32-byte stride uses only four of them)
 #ifndef LANE_CAP_PAIRS
 #define LANE_CAP_PAIRS 384 // trial pairs a particle may spend in its lane before the warp takes over (48/96/192/384: Hernquist 1.47/1.56/1.45/1.45 ms, stars 2.57/2.55/2.43/2.41)
 #endif
@@ -82,7 +87,7 @@ struct SamplerHeader {
     // (one contiguous block, staged into shared memory by ONE bulk copy)
     long long off_gas_lut;  // unsigned[NBG]: lo | hi << 16 search range per (finer) u bucket
     long long off_gas_P;    // double[n_cdf]: copy of the CDF for the search
-    long long off_gas_A;    // double4[n_cdf]: P_j, r_j, slope_j, spline piece of CDF interval j
+    long long off_gas_A;    // double[6][n_cdf]: P_j, r_j, slope_j, r_{j+1} (NaN: irregular interval), 2 pad
     long long off_gas_B;    // double[10][n_psi - 3]: brk_lo, brk_hi, aux0[4], aux1[4]
     long long gas_block_doubles;  // length of that block
     int gas_fast_ok;        // set to 0 by the prepare kernels when the packing does not apply
@@ -117,7 +122,7 @@ static SamplerHeader make_layout(const cgb_sampler_desc* d)
     if (!h.n_f) {
         h.off_gas_lut = take(NBG / 2);
         h.off_gas_P = take(h.n_cdf);
-        h.off_gas_A = take(4LL * h.n_cdf);
+        h.off_gas_A = take((long long)GAS_A_STRIDE * h.n_cdf);
         h.off_gas_B = take(10LL * (h.n_psi - 3));
         h.gas_block_doubles = o - h.off_gas_lut;
         h.gas_fast_ok = 1;
@@ -183,6 +188,30 @@ __device__ __forceinline__ int pp_walk(const double* __restrict__ brk, int nint,
     return j;
 }
 
+// pp_walk for Q independent arguments at once: the breakpoint loads of the Q walks are issued
+// together instead of one dependent chain after the other (phase 0 of the sampler is bound by
+// exactly this load latency).  Same fixed point as pp_walk: breakpoints are strictly
+// increasing, so the piece with brk[j] <= x < brk[j+1] (clamped at the ends) is unique.
+template <int Q>
+__device__ __forceinline__ void pp_walk_q(const double* __restrict__ brk, int nint, int (&j)[Q],
+                                          const double (&x)[Q])
+{
+#pragma unroll
+    for (int q = 0; q < Q; ++q) j[q] = min(max(j[q], 0), nint - 1);
+    bool moved;
+    do {
+        moved = false;
+        double b0[Q], b1[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) { b0[q] = __ldg(brk + j[q]); b1[q] = __ldg(brk + j[q] + 1); }
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            if (j[q] > 0 && x[q] < b0[q]) { --j[q]; moved = true; }
+            else if (j[q] < nint - 1 && x[q] >= b1[q]) { ++j[q]; moved = true; }
+        }
+    } while (moved);
+}
+
 // monotone bucket of a uniform in [0,1); the SAME function builds the table, so the
 // search range it yields always contains the answer
 template <int NBK = NBC>
@@ -234,10 +263,13 @@ __global__ void prep_cdf_iv_kernel(const SamplerHeader* __restrict__ hdr, double
 // Packed tables of the position-only fast path.  All radial splines of a gas / tracer sampler
 // are fitted over the model's radius grid and the CDF's r-grid is that grid (plus r = 0), so a
 // CDF interval lies inside ONE spline piece and the aux / psi splines share their breakpoints:
-// record A[j] carries np.interp's (P_j, r_j, slope_j) and that piece, record B[piece] the
+// record A[j] carries np.interp's (P_j, r_j, slope_j) and r_{j+1}, record B[piece] the
 // breakpoints and the coefficients of every spline -- two table reads per particle instead of
-// a dozen.  Where a caller's tables do not have that structure gas_fast_ok is cleared and the
-// kernel takes the general path.
+// a dozen.  For a REGULAR interval -- its spline piece is j - 2 with breakpoints exactly
+// (r_j, r_{j+1}), true of all but the first three and the last two -- the kernel needs
+// nothing but record A to place r in its piece (r < r_{j+1}: piece j - 2, dx = r - r_j);
+// the others carry NaN there and take the breakpoint walk.  Where a caller's tables do not
+// have that structure at all gas_fast_ok is cleared and the kernel takes the general path.
 __global__ void prep_gas_pack_kernel(SamplerHeader* __restrict__ hdr, double* __restrict__ base)
 {
     const SamplerHeader h = *hdr;
@@ -251,11 +283,12 @@ __global__ void prep_gas_pack_kernel(SamplerHeader* __restrict__ hdr, double* __
         const double r0 = rc[t], r1 = (t + 1 < h.n_cdf) ? rc[t + 1] : rc[t];
         const int pj = pp_find(pb, nint, r0);
         if (!(pb[pj] <= r0 || pj == 0) || !(r1 <= pb[pj + 1] || pj == nint - 1)) ok = false;
-        double4 a;
-        a.x = base[h.off_cdf_P + t]; a.y = r0; a.z = base[h.off_cdf_s + t];
-        a.w = __longlong_as_double((long long)pj);
-        ((double4*)(base + h.off_gas_A))[t] = a;
-        base[h.off_gas_P + t] = a.x;
+        const bool regular = t + 1 < h.n_cdf && pj == t - 2 && pb[pj] == r0 && pb[pj + 1] == r1 && r1 > r0;
+        double* A = base + h.off_gas_A + (long long)GAS_A_STRIDE * t;
+        A[0] = base[h.off_cdf_P + t]; A[1] = r0; A[2] = base[h.off_cdf_s + t];
+        A[3] = regular ? r1 : __longlong_as_double(0x7ff8000000000000LL);
+        A[4] = 0.0; A[5] = 0.0;
+        base[h.off_gas_P + t] = A[0];
     }
     if (t < nint) {
         double* B = base + h.off_gas_B + 10LL * t;
@@ -733,37 +766,78 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
         const int cnt = (int)min((long long)TILE, n_local - loc0);
         const long long id0 = id_base + loc0;
         int nonpos = 0;
-        for (int i = lane; i < cnt; i += 32) {
-            double psi, vesc, env;
-            const int s = b * TILE + i;
-            if (MODE == 0) {
-                const unsigned long long id = (unsigned long long)(id0 + i);
-                double u;
-                if (HOST_U && p.hu.d_u_r) u = p.hu.d_u_r[loc0 + i];
-                else {
-                    const Philox4 w = philox_rk(p.rk, (unsigned)id, (unsigned)(id >> 32), 0u, CGB_STREAM_RADIUS);
-                    u = u52(w.x, w.y);
+        if (MODE == 0) {
+            // PH0_Q particles per lane at a time: the table walks below are chains of dependent
+            // L1/L2 loads (ncu: 31 % of the kernel's warp samples sat here at 13 % of its
+            // instructions, 56 % of them long-scoreboard), so independent chains are interleaved
+            for (int i0 = lane; i0 < cnt; i0 += 32 * PH0_Q) {
+                double u[PH0_Q], r[PH0_Q], psi[PH0_Q], env[PH0_Q];
+                int lo[PH0_Q], hi[PH0_Q], jp[PH0_Q], jf[PH0_Q];
+#pragma unroll
+                for (int q = 0; q < PH0_Q; ++q) {
+                    const int ic = min(i0 + 32 * q, cnt - 1);  // lanes past the end redo the last particle
+                    const unsigned long long id = (unsigned long long)(id0 + ic);
+                    if (HOST_U && p.hu.d_u_r) u[q] = p.hu.d_u_r[loc0 + ic];
+                    else {
+                        const Philox4 w = philox_rk(p.rk, (unsigned)id, (unsigned)(id >> 32), 0u, CGB_STREAM_RADIUS);
+                        u[q] = u52(w.x, w.y);
+                    }
                 }
                 // np.interp(u, P_r, r): j = searchsorted(P_r, u, 'right') - 1        (utils.py:165)
-                const int j = cdf_find(T, u);
-                const double r = __dadd_rn(
-                    __dmul_rn(__ldg(T.cdf_s + j), __dsub_rn(u, __ldg(T.cdf_P + j))), __ldg(T.cdf_r + j));
+#pragma unroll
+                for (int q = 0; q < PH0_Q; ++q) {
+                    const unsigned lh = __ldg(T.cdf_lut + cdf_bucket<NBC>(u[q]));
+                    lo[q] = (int)(lh & 0xffffu); hi[q] = (int)(lh >> 16);
+                }
+                bool open;
+                do {
+                    open = false;
+#pragma unroll
+                    for (int q = 0; q < PH0_Q; ++q) {
+                        if (lo[q] < hi[q]) {
+                            const int mid = (lo[q] + hi[q] + 1) >> 1;
+                            if (__ldg(T.cdf_P + mid) <= u[q]) lo[q] = mid; else hi[q] = mid - 1;
+                            open = open || lo[q] < hi[q];
+                        }
+                    }
+                } while (open);
+#pragma unroll
+                for (int q = 0; q < PH0_Q; ++q) {
+                    const int j = lo[q];
+                    const int2 iv = __ldg(T.cdf_iv + j);
+                    r[q] = __dadd_rn(__dmul_rn(__ldg(T.cdf_s + j), __dsub_rn(u[q], __ldg(T.cdf_P + j))),
+                                     __ldg(T.cdf_r + j));
+                    jp[q] = iv.x; jf[q] = iv.y;
+                }
                 // psi = energy_spline(r); vesc = 2 psi; fv2esc = vesc * f(psi); vesc = sqrt(vesc)
                 //                                                           (virial.py:191-194)
-                const int2 iv = __ldg(T.cdf_iv + j);
-                psi = pp_eval_at(T.psi_brk, T.psi_pp, pp_walk(T.psi_brk, T.n_psi_int, iv.x, r), r);
-                const double ve2 = __dmul_rn(2.0, psi);
-                env = __dmul_rn(ve2, pp_eval_at(T.f_brk, T.f_pp, pp_walk(T.f_brk, T.n_f_int, iv.y, psi), psi));
-                vesc = sqrt(ve2);
-                s_rad[s] = r;
-            } else {
-                psi = p.in_psi[loc0 + i];
-                vesc = p.in_vesc[loc0 + i];
-                env = p.in_env[loc0 + i];
+                pp_walk_q<PH0_Q>(T.psi_brk, T.n_psi_int, jp, r);
+#pragma unroll
+                for (int q = 0; q < PH0_Q; ++q) psi[q] = pp_eval_at(T.psi_brk, T.psi_pp, jp[q], r[q]);
+                pp_walk_q<PH0_Q>(T.f_brk, T.n_f_int, jf, psi);
+#pragma unroll
+                for (int q = 0; q < PH0_Q; ++q)
+                    env[q] = __dmul_rn(__dmul_rn(2.0, psi[q]), pp_eval_at(T.f_brk, T.f_pp, jf[q], psi[q]));
+#pragma unroll
+                for (int q = 0; q < PH0_Q; ++q) {
+                    const int i = i0 + 32 * q;
+                    if (i < cnt) {
+                        const int s = b * TILE + i;
+                        const double vesc = sqrt(__dmul_rn(2.0, psi[q]));
+                        s_rad[s] = r[q]; s_psi[s] = psi[q]; s_ves[s] = vesc;
+                        s_es[s] = screen_es(psi[q], vesc, env[q], T.f_scale);
+                        if (!(env[q] > 0.0)) ++nonpos;
+                    }
+                }
             }
-            s_psi[s] = psi; s_ves[s] = vesc;
-            s_es[s] = screen_es(psi, vesc, env, T.f_scale);
-            if (!(env > 0.0)) ++nonpos;
+        } else {
+            for (int i = lane; i < cnt; i += 32) {
+                const int s = b * TILE + i;
+                const double psi = p.in_psi[loc0 + i], vesc = p.in_vesc[loc0 + i], env = p.in_env[loc0 + i];
+                s_psi[s] = psi; s_ves[s] = vesc;
+                s_es[s] = screen_es(psi, vesc, env, T.f_scale);
+                if (!(env > 0.0)) ++nonpos;
+            }
         }
         nonpos = __reduce_add_sync(FULL, nonpos);
         if (lane == 0 && nonpos) s_mom[11] += (double)nonpos;
@@ -1541,7 +1615,7 @@ cgb_gas_smem_kernel(const __grid_constant__ SampleParams p, void* aux0, void* au
     const double* const sm = (const double*)smem;
     const unsigned* const lut = (const unsigned*)sm;
     const double* const cdf_P = sm + (hdr->off_gas_P - hdr->off_gas_lut);
-    const double4* const tabA = (const double4*)(sm + (hdr->off_gas_A - hdr->off_gas_lut));
+    const double* const tabA = sm + (hdr->off_gas_A - hdr->off_gas_lut);
     const double* const tabB = sm + (hdr->off_gas_B - hdr->off_gas_lut);
     const double* const ps_brk = p.base + hdr->off_psi_brk;
     const double* const ps_pp = p.base + hdr->off_psi_pp;
@@ -1591,18 +1665,19 @@ cgb_gas_smem_kernel(const __grid_constant__ SampleParams p, void* aux0, void* au
         double r[2], px[2], py[2], pz[2], v0[2], v1[2], vp[2];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-            const double4 a = tabA[lo[q]];
-            r[q] = __dadd_rn(__dmul_rn(a.z, __dsub_rn(u[q], a.x)), a.y);
-            int pj = (int)__double_as_longlong(a.w);
-            const double* B = tabB + 10 * pj;
-            double2 bk = *(const double2*)B;
-            if ((r[q] >= bk.y && pj < npi - 1) || (r[q] < bk.x && pj > 0)) {
-                // r rounded onto (or past) a breakpoint: the piece FITPACK's interval search picks
+            const double2 a01 = *(const double2*)(tabA + GAS_A_STRIDE * lo[q]);      // P_j, r_j
+            const double2 a23 = *(const double2*)(tabA + GAS_A_STRIDE * lo[q] + 2);  // slope_j, r_{j+1} | NaN
+            r[q] = __dadd_rn(__dmul_rn(a23.x, __dsub_rn(u[q], a01.x)), a01.y);
+            int pj = lo[q] - 2;
+            double brk_lo = a01.y;
+            if (!(r[q] < a23.y)) {
+                // irregular interval, or r rounded onto the next breakpoint: the piece FITPACK's
+                // interval search picks
                 pj = pp_walk(ps_brk, npi, pj, r[q]);
-                B = tabB + 10 * pj;
-                bk = *(const double2*)B;
+                brk_lo = tabB[10 * pj];
             }
-            const double dx = r[q] - bk.x;
+            const double* B = tabB + 10 * pj;
+            const double dx = r[q] - brk_lo;
             if (aux0) {
                 const double2 c01 = *(const double2*)(B + 2), c23 = *(const double2*)(B + 4);
                 v0[q] = fma(fma(fma(c23.y, dx, c23.x), dx, c01.y), dx, c01.x);

@@ -15,6 +15,40 @@ void cgb_set_error(const char* fmt, ...)
 extern "C" int cgb_version(void) { return CGB_VERSION; }
 extern "C" const char* cgb_last_error(void) { return g_err; }
 
+// Bounds-checked build (make checked, -DCGB_BOUNDS_CHECK): every table / tile-buffer / output
+// index of the kernels is asserted on the device.  cgb_bounds_check_enabled says which build
+// this is; cgb_test_bounds_check launches one thread that checks index i against size n and
+// reports whether the device trapped -- the control that proves the asserts are live (a trap
+// leaves the CUDA context unusable, so run it in a process of its own).
+extern "C" int cgb_bounds_check_enabled(void)
+{
+#ifdef CGB_BOUNDS_CHECK
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+__global__ void cgb_bounds_probe_kernel(long long i, long long n, int* out)
+{
+    CGB_CHECK_INDEX(i, n);
+    *out = 1;
+}
+
+extern "C" int cgb_test_bounds_check(long long i, long long n)
+{
+    int* d = nullptr;
+    CGB_CUDA_CHECK(cudaMalloc(&d, sizeof(int)));
+    cgb_bounds_probe_kernel<<<1, 1>>>(i, n, d);
+    const cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        cgb_set_error("cgb_test_bounds_check: index %lld of %lld trapped: %s", i, n, cudaGetErrorString(e));
+        return CGB_E_CUDA;
+    }
+    CGB_CUDA_CHECK(cudaFree(d));
+    return CGB_OK;
+}
+
 extern "C" int cgb_device_sm_count(int* sm_count)
 {
     CGB_REQUIRE(sm_count != nullptr, "cgb_device_sm_count: null pointer");

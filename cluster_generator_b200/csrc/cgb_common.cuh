@@ -29,6 +29,20 @@ void cgb_set_error(const char* fmt, ...);
         }                                                                             \
     } while (0)
 
+// ---------------------------------------------------------------------------
+// `make checked` (-DCGB_BOUNDS_CHECK) turns every table / tile-buffer / output index of the
+// kernels into a device-side assert: the build the bounds test runs, since compute-sanitizer
+// is not available on the GPU pool.  Compiles to nothing in the shipped library.
+// ---------------------------------------------------------------------------
+#ifdef CGB_BOUNDS_CHECK
+#include <assert.h>
+#define CGB_CHECK_INDEX(i, n) assert((long long)(i) >= 0 && (long long)(i) < (long long)(n))
+#define CGB_CHECK(cond) assert(cond)
+#else
+#define CGB_CHECK_INDEX(i, n) ((void)0)
+#define CGB_CHECK(cond) ((void)0)
+#endif
+
 static inline size_t cgb_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---------------------------------------------------------------------------
@@ -68,6 +82,7 @@ __device__ __forceinline__ int cgb_find_interval(const double* __restrict__ t, i
         const int mid = (lo + hi) >> 1;
         if (t[mid] <= x) lo = mid; else hi = mid;
     }
+    CGB_CHECK(n < 8 || (lo >= 3 && lo <= n - 5));
     return lo;
 }
 

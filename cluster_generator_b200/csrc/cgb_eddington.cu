@@ -333,7 +333,9 @@ __device__ void dqpsrt_dev(int limit, int last, int& maxerr, double& ermax, cons
         }
     }
     __syncwarp();
+    CGB_CHECK(nrmax >= 1 && nrmax <= last);
     maxerr = iord[nrmax];
+    CGB_CHECK(maxerr >= 1 && maxerr <= last);
     ermax = elist[maxerr];
 }
 
@@ -386,6 +388,7 @@ __device__ int dqagse_warp(const F& f, double a, double b, double epsabs, double
 
     bool goto115 = false;
     for (last = 2; last <= limit; ++last) {
+        CGB_CHECK(limit <= QAGS_LIMIT && maxerr >= 1 && maxerr < last);
         a1 = alist[maxerr]; b1 = 0.5 * (alist[maxerr] + blist[maxerr]); a2 = b1; b2 = blist[maxerr];
         erlast = errmax;
         dqk21_warp(f, a1, b1, area1, error1, resabs, defab1);
@@ -449,6 +452,7 @@ __device__ int dqagse_warp(const F& f, double a, double b, double epsabs, double
         }
         ++numrl2;
         __syncwarp();
+        CGB_CHECK_INDEX(numrl2 - 1, 52);
         rlist2[numrl2 - 1] = area;
         __syncwarp();
         dqelg_dev(numrl2, rlist2, reseps, abseps, S.res3la, nres);

@@ -40,6 +40,7 @@ __device__ __forceinline__ int rs_find(const double* __restrict__ brk, int nint,
 __device__ __forceinline__ double rs_eval(const double* __restrict__ ws, int n, int j, double x)
 {
     const long long off = ((long long)(n - 2) + 31) / 32 * 32;
+    CGB_CHECK_INDEX(j, n - 3);
     const double dx = x - __ldg(ws + j);
     const double* pp = ws + off + 4 * (long long)j;
     const double2 a01 = __ldg((const double2*)pp), a23 = __ldg((const double2*)pp + 1);
@@ -291,6 +292,7 @@ __global__ void __launch_bounds__(256) cgb_map_field_kernel(const __grid_constan
                             const double wz = d ? tz : __dsub_rn(1.0, tz);
                             const double w = __dmul_rn(__dmul_rn(wx, wy), wz);
                             const size_t idx = ((size_t)(ix + a) * p.ny + (size_t)(iy + b)) * p.nz + (size_t)(iz + d);
+                            CGB_CHECK(ix + a < p.nx && iy + b < p.ny && iz + d < p.nz && ix >= 0 && iy >= 0 && iz >= 0);
                             v = __dadd_rn(v, __dmul_rn(w, __ldg(f + idx)));
                         }
             }

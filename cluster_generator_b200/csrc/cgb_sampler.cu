@@ -167,6 +167,7 @@ __device__ __forceinline__ int pp_find(const double* __restrict__ brk, int nint,
 __device__ __forceinline__ double pp_eval_at(const double* __restrict__ brk,
                                              const double* __restrict__ pp, int j, double x)
 {
+    CGB_CHECK(j >= 0);
     const double dx = x - __ldg(brk + j);
     const double2 a01 = __ldg((const double2*)(pp + 4 * (size_t)j));
     const double2 a23 = __ldg((const double2*)(pp + 4 * (size_t)j) + 1);
@@ -544,8 +545,10 @@ __device__ __forceinline__ int cdf_find(const Tables& T, double u)
     int lo = (int)(lh & 0xffffu), hi = (int)(lh >> 16);
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
+        CGB_CHECK_INDEX(mid, T.n_cdf);
         if (__ldg(T.cdf_P + mid) <= u) lo = mid; else hi = mid - 1;
     }
+    CGB_CHECK_INDEX(lo, T.n_cdf);
     return lo;
 }
 
@@ -625,6 +628,7 @@ __device__ __forceinline__ int screen_trial(const float2* __restrict__ s_screen,
     const float e = fmaf(-0.5f, v2, ps);
     const unsigned b = (unsigned)__float2int_rd(e * inv_w_f);  // negative -> huge -> sentinel
     const float B = __uint2float_rn(wb) * es;
+    CGB_CHECK_INDEX(min(b, (unsigned)NB), NB + 1);
     const float2 fb = s_screen[min(b, (unsigned)NB)];
     if (fb.y * v2 < B) return 0;
     if (fb.x * v2 >= B) return 1;
@@ -796,6 +800,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
                     for (int q = 0; q < PH0_Q; ++q) {
                         if (lo[q] < hi[q]) {
                             const int mid = (lo[q] + hi[q] + 1) >> 1;
+                            CGB_CHECK_INDEX(mid, T.n_cdf);
                             if (__ldg(T.cdf_P + mid) <= u[q]) lo[q] = mid; else hi[q] = mid - 1;
                             open = open || lo[q] < hi[q];
                         }
@@ -804,6 +809,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
 #pragma unroll
                 for (int q = 0; q < PH0_Q; ++q) {
                     const int j = lo[q];
+                    CGB_CHECK_INDEX(j, T.n_cdf);
                     const int2 iv = __ldg(T.cdf_iv + j);
                     r[q] = __dadd_rn(__dmul_rn(__ldg(T.cdf_s + j), __dsub_rn(u[q], __ldg(T.cdf_P + j))),
                                      __ldg(T.cdf_r + j));
@@ -813,16 +819,22 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
                 //                                                           (virial.py:191-194)
                 pp_walk_q<PH0_Q>(T.psi_brk, T.n_psi_int, jp, r);
 #pragma unroll
-                for (int q = 0; q < PH0_Q; ++q) psi[q] = pp_eval_at(T.psi_brk, T.psi_pp, jp[q], r[q]);
+                for (int q = 0; q < PH0_Q; ++q) {
+                    CGB_CHECK_INDEX(jp[q], T.n_psi_int);
+                    psi[q] = pp_eval_at(T.psi_brk, T.psi_pp, jp[q], r[q]);
+                }
                 pp_walk_q<PH0_Q>(T.f_brk, T.n_f_int, jf, psi);
 #pragma unroll
-                for (int q = 0; q < PH0_Q; ++q)
+                for (int q = 0; q < PH0_Q; ++q) {
+                    CGB_CHECK_INDEX(jf[q], T.n_f_int);
                     env[q] = __dmul_rn(__dmul_rn(2.0, psi[q]), pp_eval_at(T.f_brk, T.f_pp, jf[q], psi[q]));
+                }
 #pragma unroll
                 for (int q = 0; q < PH0_Q; ++q) {
                     const int i = i0 + 32 * q;
                     if (i < cnt) {
                         const int s = b * TILE + i;
+                        CGB_CHECK_INDEX(s, NBUF * TILE);
                         const double vesc = sqrt(__dmul_rn(2.0, psi[q]));
                         s_rad[s] = r[q]; s_psi[s] = psi[q]; s_ves[s] = vesc;
                         s_es[s] = screen_es(psi[q], vesc, env[q], T.f_scale);
@@ -833,6 +845,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
         } else {
             for (int i = lane; i < cnt; i += 32) {
                 const int s = b * TILE + i;
+                CGB_CHECK_INDEX(s, NBUF * TILE);
+                CGB_CHECK_INDEX(loc0 + i, n_local);
                 const double psi = p.in_psi[loc0 + i], vesc = p.in_vesc[loc0 + i], env = p.in_env[loc0 + i];
                 s_psi[s] = psi; s_ves[s] = vesc;
                 s_es[s] = screen_es(psi, vesc, env, T.f_scale);
@@ -859,6 +873,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
         for (int i = lane; i < cnt; i += 32) {
             const int s = b * TILE + i;
             const long long loc = loc0 + i;
+            CGB_CHECK_INDEX(s, NBUF * TILE);
+            CGB_CHECK_INDEX(loc, n_local);
+            CGB_CHECK(MODE == 1 || p.ld >= n_local);
             const double psi = s_psi[s];
             const int nt = s_tri[s];
             const bool deferred = nt == TRI_DEFERRED;  // speed comes from cgb_hard_kernel
@@ -962,6 +979,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
         const float cps = __shfl_sync(FULL, ps, src), cvs = __shfl_sync(FULL, vs, src),
                     ces = __shfl_sync(FULL, es, src);
         const unsigned cid_lo = __shfl_sync(FULL, id_lo, src), cid_hi = __shfl_sync(FULL, id_hi, src);
+        CGB_CHECK_INDEX(s, NBUF * TILE);
         const double* penv = env_ptr(s);
         unsigned long long pr = p0;
         for (;;) {
@@ -1007,6 +1025,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
                         HardEntry* e = (HardEntry*)(p.scratch + 1) + h;
                         e->id = ((unsigned long long)cid_hi << 32) | cid_lo;
                         e->loc = BGET(b_loc0, bb) + (s - bb * TILE);
+                        CGB_CHECK_INDEX(e->loc, n_local);
                         e->psi = s_psi[s]; e->vesc = s_ves[s];
                         e->env = penv ? *penv : envelope_of(T, s_psi[s]);
                         e->next_pair = pr; e->best = ~0ULL;
@@ -1102,6 +1121,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
                     cur_next += __popc(need);
                     if (slot < 0 && i < cur_cnt) {
                         slot = cur * TILE + i;
+                        CGB_CHECK_INDEX(slot, NBUF * TILE);
                         ps = (float)s_psi[slot];
                         vs = (float)(s_ves[slot] * 0x1.0p-32);
                         es = s_es[slot];
@@ -1230,6 +1250,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
                     acc = r.acc;
                 }
                 if (acc) {
+                    CGB_CHECK_INDEX(slot, NBUF * TILE);
+                    CGB_CHECK(ntr >= 1u);
                     s_wa[slot] = wacc;
                     s_tri[slot] = (int)ntr;
                     done_oth = (slot >= TILE) != (cur == 1);
@@ -1352,6 +1374,7 @@ __global__ void __launch_bounds__(512, 1) cgb_hard_kernel(const __grid_constant_
         const unsigned long long e_id = ent[h].id;
         const double e_vesc = ent[h].vesc;
         const long long loc = ent[h].loc;
+        CGB_CHECK_INDEX(loc, p.id_end - p.id_begin);
         const unsigned long long best = *(volatile unsigned long long*)&ent[h].best;
         double v;
         int nt;
@@ -1520,6 +1543,7 @@ __global__ void __launch_bounds__(256) cgb_gas_kernel(const __grid_constant__ Sa
         int jw[2];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
+            CGB_CHECK_INDEX(lo[q], hdr->n_cdf);
             r[q] = __dadd_rn(__dmul_rn(__ldg(cdf_s + lo[q]), __dsub_rn(u[q], __ldg(cdf_P + lo[q]))),
                              __ldg(cdf_r + lo[q]));
             jw[q] = __ldg(cdf_iv + lo[q]).x;  // starting piece for every spline over `radius`
@@ -1530,6 +1554,8 @@ __global__ void __launch_bounds__(256) cgb_gas_kernel(const __grid_constant__ Sa
             const double rs = __dmul_rn(r[q], st);
             px[q] = __dmul_rn(rs, cp); py[q] = __dmul_rn(rs, sp); pz[q] = __dmul_rn(r[q], ct);
         }
+        CGB_CHECK_INDEX(loc + (both ? 1 : 0), n_local);
+        CGB_CHECK(p.ld >= n_local);
         store_pair<OutT>(p.pos, loc, px[0], px[1], both, vec);
         store_pair<OutT>(p.pos, p.ld + loc, py[0], py[1], both, vec);
         store_pair<OutT>(p.pos, 2 * p.ld + loc, pz[0], pz[1], both, vec);
@@ -1658,6 +1684,7 @@ cgb_gas_smem_kernel(const __grid_constant__ SampleParams p, void* aux0, void* au
             for (int q = 0; q < 2; ++q) {
                 if (lo[q] < hi[q]) {
                     const int mid = (lo[q] + hi[q] + 1) >> 1;
+                    CGB_CHECK_INDEX(mid, hdr->n_cdf);
                     if (cdf_P[mid] <= u[q]) lo[q] = mid; else hi[q] = mid - 1;
                 }
             }
@@ -1665,6 +1692,7 @@ cgb_gas_smem_kernel(const __grid_constant__ SampleParams p, void* aux0, void* au
         double r[2], px[2], py[2], pz[2], v0[2], v1[2], vp[2];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
+            CGB_CHECK_INDEX(lo[q], hdr->n_cdf);
             const double2 a01 = *(const double2*)(tabA + GAS_A_STRIDE * lo[q]);      // P_j, r_j
             const double2 a23 = *(const double2*)(tabA + GAS_A_STRIDE * lo[q] + 2);  // slope_j, r_{j+1} | NaN
             r[q] = __dadd_rn(__dmul_rn(a23.x, __dsub_rn(u[q], a01.x)), a01.y);
@@ -1676,6 +1704,7 @@ cgb_gas_smem_kernel(const __grid_constant__ SampleParams p, void* aux0, void* au
                 pj = pp_walk(ps_brk, npi, pj, r[q]);
                 brk_lo = tabB[10 * pj];
             }
+            CGB_CHECK_INDEX(pj, npi);
             const double* B = tabB + 10 * pj;
             const double dx = r[q] - brk_lo;
             if (aux0) {
@@ -1694,6 +1723,8 @@ cgb_gas_smem_kernel(const __grid_constant__ SampleParams p, void* aux0, void* au
             const double rs = __dmul_rn(r[q], st);
             px[q] = __dmul_rn(rs, cp); py[q] = __dmul_rn(rs, sp); pz[q] = __dmul_rn(r[q], ct);
         }
+        CGB_CHECK_INDEX(loc + (both ? 1 : 0), n_local);
+        CGB_CHECK(p.ld >= n_local);
         store_pair<OutT>(p.pos, loc, px[0], px[1], both, vec);
         store_pair<OutT>(p.pos, p.ld + loc, py[0], py[1], both, vec);
         store_pair<OutT>(p.pos, 2 * p.ld + loc, pz[0], pz[1], both, vec);

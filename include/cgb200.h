@@ -98,6 +98,17 @@ int cgb_test_div_by_rcp(const double *d_x, const double *d_b, double *d_q, int64
 /* Profiling hook: clock64 ticks of the four phases (serial prologue, register-window run, serial
  * epilogue, back-substitution) of the last FITPACK-exact fit: [0..3] factorising, [4..7] re-using. */
 int cgb_test_givens_cycles(long long *host8);
+
+/* Bounds-checked build (`make -C cluster_generator_b200/csrc checked` -> libcgb200_checked.so,
+ * -DCGB_BOUNDS_CHECK): every table, tile-buffer and output index of the kernels is a device-side
+ * assert.  It stands in for compute-sanitizer, which the GPU pool does not offer; the reference
+ * has no counterpart (its loops are numpy / Cython with Python's own bounds checks).
+ * cgb_bounds_check_enabled: 1 in that build, 0 in the shipped library.
+ * cgb_test_bounds_check: one device thread checks index i against size n; CGB_OK when the
+ * device did not trap (always, in the shipped library), CGB_E_CUDA when it did -- after which
+ * the process's CUDA context is unusable, so call it from a process of its own. */
+int cgb_bounds_check_enabled(void);
+int cgb_test_bounds_check(long long i, long long n);
 /* Evaluate the spline (nu = 0) or its first derivative (nu = 1) at m points
  * (FITPACK splev/splder arithmetic, extrapolating outside the knots). */
 int cgb_spline_eval(const double *d_t, const double *d_c, int n, const double *d_x, double *d_y,

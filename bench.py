@@ -693,7 +693,7 @@ def run_cuda(args):
     }
     # the gas kernel (HBM-write bound: 72 B per particle incl. the zero velocities)
     gas_s = g_ms * 1e-3
-    roofline["gas_kernel"] = {"kernel": "cgb_gas_kernel<double,false>", "bound": "hbm", "kernel_ms": g_ms,
+    roofline["gas_kernel"] = {"kernel": "cgb_gas_smem_kernel<double,false>", "bound": "hbm", "kernel_ms": g_ms,
                               "achieved": n * B_GAS / gas_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                               "frac": n * B_GAS / gas_s / 1e9 / hbm_peak, "particles_per_s": n / gas_s}
 
@@ -725,7 +725,7 @@ def run_cuda(args):
                 "steps": e2e_steps, "roofline": e2e_roofline,
                 "what": "ClusterModel.generate_dm_particles + generate_gas_particles(host=True) from host tables: chunked generation, every chunk's D2H copy to pinned host memory overlapped with the next chunk's kernels; gas velocities (identically zero) are host-side zeros"},
         "configs": configs,
-        # per step: cgb_sample_kernel + cgb_hard_kernel (deferred long-tail pass) + cgb_gas_kernel
+        # per step: cgb_sample_kernel + cgb_hard_kernel (deferred long-tail pass) + cgb_gas_smem_kernel
         "gpu_launches": 3 * args.steps,
         "roofline": roofline,
         "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port",

@@ -619,8 +619,38 @@ __device__ __forceinline__ void sincos2pi(double u, double* sn, double* cs)
     *cs = __hiloint2double(__double2hiint(c) ^ (((q + 1) & 2) << 30), __double2loint(c));
 }
 
+// Shared-memory accesses of the trial loop by 32-bit shared-window address held in a register
+// the compiler cannot see through: given a pointer it re-derives the window base
+// (S2UR SR_CgaCtaId + ULEA) at every use -- three times per loop iteration, with the S2UR
+// latency exposed each time.
+struct ScreenAddr { unsigned a; };
+__device__ __forceinline__ float2 screen_load(const float2* __restrict__ s, unsigned idx) { return s[idx]; }
+__device__ __forceinline__ float2 screen_load(ScreenAddr s, unsigned idx)
+{
+    float2 v;
+    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(s.a + idx * 8u));
+    return v;
+}
+__device__ __forceinline__ double lds_f64(unsigned a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds_f32(unsigned a)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(unsigned a, unsigned v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
 // fp32 screen: 0 = reject, 1 = accept, 2 = undecided.
-__device__ __forceinline__ int screen_trial(const float2* __restrict__ s_screen, float inv_w_f,
+template <typename ScreenRef>
+__device__ __forceinline__ int screen_trial(ScreenRef s_screen, float inv_w_f,
                                             unsigned wa, unsigned wb, float ps, float vs, float es)
 {
     const float v = __uint2float_rn(wa) * vs;
@@ -629,7 +659,7 @@ __device__ __forceinline__ int screen_trial(const float2* __restrict__ s_screen,
     const unsigned b = (unsigned)__float2int_rd(e * inv_w_f);  // negative -> huge -> sentinel
     const float B = __uint2float_rn(wb) * es;
     CGB_CHECK_INDEX(min(b, (unsigned)NB), NB + 1);
-    const float2 fb = s_screen[min(b, (unsigned)NB)];
+    const float2 fb = screen_load(s_screen, min(b, (unsigned)NB));
     if (fb.y * v2 < B) return 0;
     if (fb.x * v2 >= B) return 1;
     return 2;
@@ -676,7 +706,8 @@ __device__ __forceinline__ PairResult decide_pair(const Tables& T, const Philox4
 }
 
 // evaluate the two trials of one Philox call for one particle
-__device__ __forceinline__ PairResult eval_pair(const Tables& T, const float2* s_screen,
+template <typename ScreenRef>
+__device__ __forceinline__ PairResult eval_pair(const Tables& T, ScreenRef s_screen,
                                                 const Philox4& w, float ps, float vs, float es,
                                                 const double* ppsi, const double* pvesc,
                                                 const double* penv)
@@ -733,6 +764,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
     double* s_mom = (double*)(smem + SCREEN_BYTES + (size_t)WARPS * (NBUF * TILE) * 32) + (size_t)warp * CGB_NMOMENTS;
     const unsigned FULL = 0xffffffffu;
     const unsigned lt_mask = (1u << lane) - 1u;
+    // the same arrays by shared-window address, opaque to the compiler (see ScreenAddr)
+    ScreenAddr scr;
+    scr.a = (unsigned)__cvta_generic_to_shared(s_screen);
+    unsigned a_psi = (unsigned)__cvta_generic_to_shared(s_psi), a_ves = (unsigned)__cvta_generic_to_shared(s_ves),
+             a_es = (unsigned)__cvta_generic_to_shared(s_es), a_wa = (unsigned)__cvta_generic_to_shared(s_wa);
+    asm volatile("" : "+r"(scr.a), "+r"(a_psi), "+r"(a_ves), "+r"(a_es), "+r"(a_wa));
 
     __shared__ unsigned long long s_mbar;
     Tables T;
@@ -994,11 +1031,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
             if (two && mine1 <= 0xFFFFFFFFull) {
                 w0 = philox_rk(p.rk, cid_lo, cid_hi, (unsigned)mine0, CGB_STREAM_VEL_TRIAL);
                 w1 = philox_rk(p.rk, cid_lo, cid_hi, (unsigned)mine1, CGB_STREAM_VEL_TRIAL);
-                r0 = eval_pair(T, s_screen, w0, cps, cvs, ces, s_psi + s, s_ves + s, penv);
-                r1 = eval_pair(T, s_screen, w1, cps, cvs, ces, s_psi + s, s_ves + s, penv);
+                r0 = eval_pair(T, scr, w0, cps, cvs, ces, s_psi + s, s_ves + s, penv);
+                r1 = eval_pair(T, scr, w1, cps, cvs, ces, s_psi + s, s_ves + s, penv);
             } else if (mine0 <= 0xFFFFFFFFull) {
                 w0 = philox_rk(p.rk, cid_lo, cid_hi, (unsigned)mine0, CGB_STREAM_VEL_TRIAL);
-                r0 = eval_pair(T, s_screen, w0, cps, cvs, ces, s_psi + s, s_ves + s, penv);
+                r0 = eval_pair(T, scr, w0, cps, cvs, ces, s_psi + s, s_ves + s, penv);
             }
             m_exact += r0.n_exact + r1.n_exact;
             const unsigned hit0 = __ballot_sync(FULL, r0.acc != 0);
@@ -1122,9 +1159,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
                     if (slot < 0 && i < cur_cnt) {
                         slot = cur * TILE + i;
                         CGB_CHECK_INDEX(slot, NBUF * TILE);
-                        ps = (float)s_psi[slot];
-                        vs = (float)(s_ves[slot] * 0x1.0p-32);
-                        es = s_es[slot];
+                        ps = (float)lds_f64(a_psi + 8u * (unsigned)slot);
+                        vs = (float)(lds_f64(a_ves + 8u * (unsigned)slot) * 0x1.0p-32);
+                        es = lds_f32(a_es + 4u * (unsigned)slot);
                         pair = 0;
                         id_lo = cur_id0_lo + (unsigned)i;
                         id_hi = cur_id0_hi + (id_lo < cur_id0_lo ? 1u : 0u);
@@ -1178,19 +1215,19 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
                 // screen every trial of the iteration up front (independent fp32 chains), then
                 // take the first accepted one; any undecided trial sends the lane to the
                 // sequential path below
-                const int t0 = screen_trial(s_screen, T.inv_w_f, w0.x, w0.y, ps, vs, es);
-                const int t1 = screen_trial(s_screen, T.inv_w_f, w0.z, w0.w, ps, vs, es);
-                const int t2 = screen_trial(s_screen, T.inv_w_f, w1.x, w1.y, ps, vs, es);
-                const int t3 = screen_trial(s_screen, T.inv_w_f, w1.z, w1.w, ps, vs, es);
+                const int t0 = screen_trial(scr, T.inv_w_f, w0.x, w0.y, ps, vs, es);
+                const int t1 = screen_trial(scr, T.inv_w_f, w0.z, w0.w, ps, vs, es);
+                const int t2 = screen_trial(scr, T.inv_w_f, w1.x, w1.y, ps, vs, es);
+                const int t3 = screen_trial(scr, T.inv_w_f, w1.z, w1.w, ps, vs, es);
                 int any = t0 | t1 | t2 | t3;
 #if LEAN_PAIRS >= 3
-                const int t4 = screen_trial(s_screen, T.inv_w_f, w2.x, w2.y, ps, vs, es);
-                const int t5 = screen_trial(s_screen, T.inv_w_f, w2.z, w2.w, ps, vs, es);
+                const int t4 = screen_trial(scr, T.inv_w_f, w2.x, w2.y, ps, vs, es);
+                const int t5 = screen_trial(scr, T.inv_w_f, w2.z, w2.w, ps, vs, es);
                 any |= t4 | t5;
 #endif
 #if LEAN_PAIRS >= 4
-                const int t6 = screen_trial(s_screen, T.inv_w_f, w3.x, w3.y, ps, vs, es);
-                const int t7 = screen_trial(s_screen, T.inv_w_f, w3.z, w3.w, ps, vs, es);
+                const int t6 = screen_trial(scr, T.inv_w_f, w3.x, w3.y, ps, vs, es);
+                const int t7 = screen_trial(scr, T.inv_w_f, w3.z, w3.w, ps, vs, es);
                 any |= t6 | t7;
 #endif
                 if (!(any & 2)) {
@@ -1252,8 +1289,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
                 if (acc) {
                     CGB_CHECK_INDEX(slot, NBUF * TILE);
                     CGB_CHECK(ntr >= 1u);
-                    s_wa[slot] = wacc;
-                    s_tri[slot] = (int)ntr;
+                    sts_u32(a_wa + 4u * (unsigned)slot, wacc);
+                    sts_u32(a_es + 4u * (unsigned)slot, ntr);  // s_tri aliases s_es
                     done_oth = (slot >= TILE) != (cur == 1);
                     slot = -1;
                 } else {

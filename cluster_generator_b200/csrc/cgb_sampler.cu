@@ -694,11 +694,25 @@ __device__ __noinline__ PairResult resolve_pair(const Tables& T, Philox4 w, int 
     return r;
 }
 
+// where the exact path finds a particle's fp64 psi and vesc: by pointer, or by shared-window
+// address (tile slot), read only when a trial is undecided
+struct PsiVescPtr {
+    const double *ppsi, *pvesc;
+    __device__ __forceinline__ double psi() const { return *ppsi; }
+    __device__ __forceinline__ double vesc() const { return *pvesc; }
+};
+struct PsiVescSlot {
+    unsigned a_psi, a_ves;
+    __device__ __forceinline__ double psi() const { return lds_f64(a_psi); }
+    __device__ __forceinline__ double vesc() const { return lds_f64(a_ves); }
+};
+
 // outcome of a pair from its two screen results; the exact path only where it matters
+template <typename PV>
 __device__ __forceinline__ PairResult decide_pair(const Tables& T, const Philox4& w, int sa, int sb,
-                                                  const double* ppsi, const double* pvesc, const double* penv)
+                                                  const PV& pv, const double* penv)
 {
-    if (sa == 2 || (sa == 0 && sb == 2)) return resolve_pair(T, w, sa, sb, *ppsi, *pvesc, penv);
+    if (sa == 2 || (sa == 0 && sb == 2)) return resolve_pair(T, w, sa, sb, pv.psi(), pv.vesc(), penv);
     PairResult r;
     r.n_exact = 0;
     r.acc = (sa == 1) ? 1 : ((sb == 1) ? 2 : 0);
@@ -706,15 +720,14 @@ __device__ __forceinline__ PairResult decide_pair(const Tables& T, const Philox4
 }
 
 // evaluate the two trials of one Philox call for one particle
-template <typename ScreenRef>
+template <typename ScreenRef, typename PV>
 __device__ __forceinline__ PairResult eval_pair(const Tables& T, ScreenRef s_screen,
                                                 const Philox4& w, float ps, float vs, float es,
-                                                const double* ppsi, const double* pvesc,
-                                                const double* penv)
+                                                const PV& pv, const double* penv)
 {
     const int sa = screen_trial(s_screen, T.inv_w_f, w.x, w.y, ps, vs, es);
     const int sb = screen_trial(s_screen, T.inv_w_f, w.z, w.w, ps, vs, es);
-    return decide_pair(T, w, sa, sb, ppsi, pvesc, penv);
+    return decide_pair(T, w, sa, sb, pv, penv);
 }
 
 template <typename OutT>
@@ -1018,6 +1031,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
         const unsigned cid_lo = __shfl_sync(FULL, id_lo, src), cid_hi = __shfl_sync(FULL, id_hi, src);
         CGB_CHECK_INDEX(s, NBUF * TILE);
         const double* penv = env_ptr(s);
+        const PsiVescSlot cpv = {a_psi + 8u * (unsigned)s, a_ves + 8u * (unsigned)s};
         unsigned long long pr = p0;
         for (;;) {
             const unsigned long long mine0 = pr + lane, mine1 = pr + 32 + lane;
@@ -1031,11 +1045,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
             if (two && mine1 <= 0xFFFFFFFFull) {
                 w0 = philox_rk(p.rk, cid_lo, cid_hi, (unsigned)mine0, CGB_STREAM_VEL_TRIAL);
                 w1 = philox_rk(p.rk, cid_lo, cid_hi, (unsigned)mine1, CGB_STREAM_VEL_TRIAL);
-                r0 = eval_pair(T, scr, w0, cps, cvs, ces, s_psi + s, s_ves + s, penv);
-                r1 = eval_pair(T, scr, w1, cps, cvs, ces, s_psi + s, s_ves + s, penv);
+                r0 = eval_pair(T, scr, w0, cps, cvs, ces, cpv, penv);
+                r1 = eval_pair(T, scr, w1, cps, cvs, ces, cpv, penv);
             } else if (mine0 <= 0xFFFFFFFFull) {
                 w0 = philox_rk(p.rk, cid_lo, cid_hi, (unsigned)mine0, CGB_STREAM_VEL_TRIAL);
-                r0 = eval_pair(T, scr, w0, cps, cvs, ces, s_psi + s, s_ves + s, penv);
+                r0 = eval_pair(T, scr, w0, cps, cvs, ces, cpv, penv);
             }
             m_exact += r0.n_exact + r1.n_exact;
             const unsigned hit0 = __ballot_sync(FULL, r0.acc != 0);
@@ -1251,9 +1265,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cgb_sample_kernel(const __grid_
 #endif
                 {
 #if LEAN_SCREEN_ALL
-#define CGB_PAIR(k, w, ta, tb) decide_pair(T, w, ta, tb, s_psi + slot, s_ves + slot, env_ptr(slot))
+#define CGB_PAIR(k, w, ta, tb) decide_pair(T, w, ta, tb, PsiVescSlot{a_psi + 8u * (unsigned)slot, a_ves + 8u * (unsigned)slot}, env_ptr(slot))
 #else
-#define CGB_PAIR(k, w, ta, tb) eval_pair(T, s_screen, w, ps, vs, es, s_psi + slot, s_ves + slot, env_ptr(slot))
+#define CGB_PAIR(k, w, ta, tb) eval_pair(T, scr, w, ps, vs, es, PsiVescSlot{a_psi + 8u * (unsigned)slot, a_ves + 8u * (unsigned)slot}, env_ptr(slot))
                     const int t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0, t6 = 0, t7 = 0;
                     (void)t0; (void)t1; (void)t2; (void)t3; (void)t4; (void)t5; (void)t6; (void)t7;
 #endif
@@ -1378,7 +1392,7 @@ __global__ void __launch_bounds__(512, 1) cgb_hard_kernel(const __grid_constant_
             if (mine <= 0xFFFFFFFFull) {
                 const Philox4 w = philox_rk(p.rk, (unsigned)e_id, (unsigned)(e_id >> 32), (unsigned)mine,
                                             CGB_STREAM_VEL_TRIAL);
-                const PairResult r = eval_pair(T, s_screen, w, cps, cvs, ces, &e_psi, &e_vesc, &e_env);
+                const PairResult r = eval_pair(T, s_screen, w, cps, cvs, ces, PsiVescPtr{&e_psi, &e_vesc}, &e_env);
                 if (r.acc) t = 2ULL * mine + (unsigned)(r.acc - 1);
             }
             for (int o = 16; o; o >>= 1) {

@@ -48,18 +48,28 @@ NCU_PROFILE = os.path.join(ROOT, "profiles", "r02_ncu.json")  # written by scrip
 SAMPLER_SRC = os.path.join(ROOT, "cluster_generator_b200", "csrc", "cgb_sampler.cu")
 
 
+def code_sha256(path):
+    """sha256 of a CUDA source with comments and white space removed: the hash follows the
+    code the compiler sees, not its documentation."""
+    import hashlib
+    import re
+
+    text = open(path, encoding="utf-8").read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)   # block comments
+    text = re.sub(r"//[^\n]*", "", text)                 # line comments (no string in the sources holds "//")
+    return hashlib.sha256("".join(text.split()).encode()).hexdigest()
+
+
 def load_ncu_profile():
     """Per-launch ncu counters of the dominant kernel on THIS workload (smsp__inst_executed,
     dram bytes), captured by scripts/make_profiles.py together with the sha256 of the kernel
-    source they were measured on; `stale` when the source has changed since."""
-    import hashlib
-
+    source (code only, see code_sha256) they were measured on; `stale` when the code has
+    changed since."""
     try:
         prof = json.load(open(NCU_PROFILE))
     except Exception:
         return None
-    sha = hashlib.sha256(open(SAMPLER_SRC, "rb").read()).hexdigest()
-    prof["stale"] = prof.get("sampler_sha256") != sha
+    prof["stale"] = prof.get("sampler_sha256") != code_sha256(SAMPLER_SRC)
     return prof
 
 

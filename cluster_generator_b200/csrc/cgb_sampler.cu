@@ -15,7 +15,8 @@
 //     the index range is sharded over GPUs.
 //   * each WARP owns two rolling buffers of TILE consecutive ids, claimed from a
 //     global atomic counter.  Phase 0 (uniform): radius, psi, envelope for a whole
-//     buffer into shared memory.  Phase 1 (divergent): one particle per lane, lanes
+//     buffer into shared memory, two particles per lane at a time so that their table walks
+//     (dependent L1/L2 loads) overlap.  Phase 1 (divergent): one particle per lane, lanes
 //     refill from the buffers as they accept (ballot + popc), two trials per Philox
 //     call; the next buffer is filled while stragglers of the previous one finish.
 //     A particle that exceeds LANE_CAP_PAIRS trial pairs, or is left over when the
@@ -57,6 +58,11 @@
 #define NBUF 2             // tile buffers per warp (ring): a straggler may keep its lane for
 #endif                     // NBUF-1 tile lifetimes before the warp has to finish it.  Measured
                            // (1e7 Vikhlinin DM): 2x128 1.06 ms, 3x96 1.13, 4x64 1.15, 4x96 1.19
+// Shape sweep on the round-2 code (1e7 Vikhlinin / Hernquist, ms; shipped 16 warps x 2x128: 0.871 / 1.456):
+//   2x96 1.011 / 1.623 | 2x160 1.021 / 1.652 | 14 warps 2x192 1.217 / 1.929 | 12 warps 2x224 1.079 / 1.694
+//   20 warps at 96 registers: 2x96 1.045 / 1.591, 2x128 1.056 / 1.657 | 24 warps at 80 registers, 2x64: 1.048 / 1.735
+// (the shared-memory carve-out is quantised at 132/164/196/228 KB: every other shape either
+// shrinks L1 under the 116 KB of phase-0 tables or the tile under the stragglers)
 #define NBC 1024           // buckets of the CDF start-index table
 #define NBG 2048           // finer start-index table of the position-only (gas) fast path
 #define GAS_A_STRIDE 6      // doubles per record A: 48 B = 3 x 16 B, so consecutive records rotate through

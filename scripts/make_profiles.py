@@ -18,6 +18,8 @@ tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
 G = "gpurun_out"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 os.chdir(ROOT)
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402  (code_sha256: the hash bench.py compares against)
 
 
 def last_json(path):
@@ -87,7 +89,7 @@ if samp:
         "warp_instructions_per_launch": val('smsp__inst_executed.sum'),
         "dram_bytes_per_launch": val('dram__bytes_read.sum') + val('dram__bytes_write.sum'),
         "gpu_time_us_under_ncu": val('gpu__time_duration.sum'),
-        "sampler_sha256": hashlib.sha256(open("cluster_generator_b200/csrc/cgb_sampler.cu", "rb").read()).hexdigest(),
+        "sampler_sha256": bench.code_sha256("cluster_generator_b200/csrc/cgb_sampler.cu"),
         "source": f"gpurun_out/prof_{tag}.ncu-rep (ncu --set full --clock-control none), summarised by scripts/make_profiles.py",
     }
     json.dump(prof, open(f"profiles/{tag}_ncu.json", "w"), indent=1)

@@ -637,6 +637,24 @@ __device__ __forceinline__ float2 screen_load(ScreenAddr s, unsigned idx)
     asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(s.a + idx * 8u));
     return v;
 }
+__device__ __forceinline__ unsigned ldsc_u32(unsigned a)
+{
+    unsigned v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double ldsc_f64(unsigned a)
+{
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double2 ldsc_v2f64(unsigned a)
+{
+    double2 v;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
 __device__ __forceinline__ double lds_f64(unsigned a)
 {
     double v;
@@ -1695,11 +1713,13 @@ cgb_gas_smem_kernel(const __grid_constant__ SampleParams p, void* aux0, void* au
                 : "memory");
         }
     }
-    const double* const sm = (const double*)smem;
-    const unsigned* const lut = (const unsigned*)sm;
-    const double* const cdf_P = sm + (hdr->off_gas_P - hdr->off_gas_lut);
-    const double* const tabA = sm + (hdr->off_gas_A - hdr->off_gas_lut);
-    const double* const tabB = sm + (hdr->off_gas_B - hdr->off_gas_lut);
+    // the tables by 32-bit shared-window address, opaque to the compiler: through pointers it
+    // re-derived the window base (S2UR SR_CgaCtaId + ULEA) before each of the seven gathers
+    unsigned lut = (unsigned)__cvta_generic_to_shared(smem);
+    unsigned cdf_P = lut + 8u * (unsigned)(hdr->off_gas_P - hdr->off_gas_lut);
+    unsigned tabA = lut + 8u * (unsigned)(hdr->off_gas_A - hdr->off_gas_lut);
+    unsigned tabB = lut + 8u * (unsigned)(hdr->off_gas_B - hdr->off_gas_lut);
+    asm volatile("" : "+r"(lut), "+r"(cdf_P), "+r"(tabA), "+r"(tabB));
     const double* const ps_brk = p.base + hdr->off_psi_brk;
     const double* const ps_pp = p.base + hdr->off_psi_pp;
     const long long n_local = p.id_end - p.id_begin;
@@ -1733,7 +1753,7 @@ cgb_gas_smem_kernel(const __grid_constant__ SampleParams p, void* aux0, void* au
         int lo[2], hi[2];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-            const unsigned lh = lut[cdf_bucket<NBG>(u[q])];
+            const unsigned lh = ldsc_u32(lut + 4u * (unsigned)cdf_bucket<NBG>(u[q]));
             lo[q] = (int)(lh & 0xffffu); hi[q] = (int)(lh >> 16);
         }
         while (lo[0] < hi[0] || lo[1] < hi[1]) {
@@ -1742,7 +1762,7 @@ cgb_gas_smem_kernel(const __grid_constant__ SampleParams p, void* aux0, void* au
                 if (lo[q] < hi[q]) {
                     const int mid = (lo[q] + hi[q] + 1) >> 1;
                     CGB_CHECK_INDEX(mid, hdr->n_cdf);
-                    if (cdf_P[mid] <= u[q]) lo[q] = mid; else hi[q] = mid - 1;
+                    if (ldsc_f64(cdf_P + 8u * (unsigned)mid) <= u[q]) lo[q] = mid; else hi[q] = mid - 1;
                 }
             }
         }
@@ -1750,8 +1770,8 @@ cgb_gas_smem_kernel(const __grid_constant__ SampleParams p, void* aux0, void* au
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             CGB_CHECK_INDEX(lo[q], hdr->n_cdf);
-            const double2 a01 = *(const double2*)(tabA + GAS_A_STRIDE * lo[q]);      // P_j, r_j
-            const double2 a23 = *(const double2*)(tabA + GAS_A_STRIDE * lo[q] + 2);  // slope_j, r_{j+1} | NaN
+            const double2 a01 = ldsc_v2f64(tabA + (8u * GAS_A_STRIDE) * (unsigned)lo[q]);        // P_j, r_j
+            const double2 a23 = ldsc_v2f64(tabA + (8u * GAS_A_STRIDE) * (unsigned)lo[q] + 16u);  // slope_j, r_{j+1} | NaN
             r[q] = __dadd_rn(__dmul_rn(a23.x, __dsub_rn(u[q], a01.x)), a01.y);
             int pj = lo[q] - 2;
             double brk_lo = a01.y;
@@ -1759,17 +1779,17 @@ cgb_gas_smem_kernel(const __grid_constant__ SampleParams p, void* aux0, void* au
                 // irregular interval, or r rounded onto the next breakpoint: the piece FITPACK's
                 // interval search picks
                 pj = pp_walk(ps_brk, npi, pj, r[q]);
-                brk_lo = tabB[10 * pj];
+                brk_lo = ldsc_f64(tabB + 80u * (unsigned)pj);
             }
             CGB_CHECK_INDEX(pj, npi);
-            const double* B = tabB + 10 * pj;
+            const unsigned B = tabB + 80u * (unsigned)pj;
             const double dx = r[q] - brk_lo;
             if (aux0) {
-                const double2 c01 = *(const double2*)(B + 2), c23 = *(const double2*)(B + 4);
+                const double2 c01 = ldsc_v2f64(B + 16u), c23 = ldsc_v2f64(B + 32u);
                 v0[q] = fma(fma(fma(c23.y, dx, c23.x), dx, c01.y), dx, c01.x);
             }
             if (aux1) {
-                const double2 c01 = *(const double2*)(B + 6), c23 = *(const double2*)(B + 8);
+                const double2 c01 = ldsc_v2f64(B + 48u), c23 = ldsc_v2f64(B + 64u);
                 v1[q] = fma(fma(fma(c23.y, dx, c23.x), dx, c01.y), dx, c01.x);
             }
             if (p.pot) vp[q] = -pp_eval_at(ps_brk, ps_pp, pj, r[q]);  // same breakpoints (checked by the prepare kernel)

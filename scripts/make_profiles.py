@@ -2,6 +2,7 @@
 """Summarise one round's ncu captures from gpurun_out/ into profiles/ (tracked).
 
 usage: make_profiles.py r02
+       make_profiles.py summary <report.ncu-rep> <out.md> <title>   (the metric table of any capture)
 inputs (written by the gpurun commands in profiles/README.md):
   gpurun_out/launches_<tag>.csv     ncu --metrics gpu__time_duration.sum launch list of bench.py
   gpurun_out/prof_<tag>.ncu-rep     ncu --set full of cgb_sample_kernel / gas kernel / f(E) kernels
@@ -13,6 +14,41 @@ outputs:
                             "stale" when cgb_sampler.cu has changed since the capture.
 """
 import collections, csv, hashlib, json, os, shutil, subprocess, sys
+
+KEYS = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread',
+        'launch__shared_mem_per_block_dynamic', 'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'smsp__thread_inst_executed_per_inst_executed.ratio',
+        'dram__bytes_read.sum', 'dram__bytes_write.sum', 'dram__throughput.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__throughput.avg.pct_of_peak_sustained_active', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed',
+        'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active', 'l1tex__t_sector_pipe_lsu_mem_global_op_ld_hit_rate.pct',
+        'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum',
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio', 'smsp__warps_eligible.avg.per_cycle_active']
+
+
+def summarise(report, out_md, title):
+    """Selected metrics of the last capture of every kernel in an ncu report -> markdown."""
+    raw = subprocess.run(["ncu", "-i", report, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    r = list(csv.reader(raw.splitlines())); h, units = r[0], r[1]
+    o2 = [f"# ncu --set full, {title}", "",
+          "Raw report kept out of git; regenerate with the command in profiles/README.md. Values per launch (the last capture of each kernel).", ""]
+    last = collections.OrderedDict((row[h.index('Kernel Name')], row) for row in r[2:])
+    for row in last.values():
+        o2 += [f"## {row[h.index('Kernel Name')]}", "", "| metric | value | unit |", "|---|---:|---|"]
+        o2 += [f"| {k} | {row[h.index(k)]} | {units[h.index(k)]} |" for k in KEYS if k in h] + [""]
+    open(out_md, "w").write("\n".join(o2))
+    return h, units, last
+
+
+if len(sys.argv) > 1 and sys.argv[1] == "summary":
+    summarise(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else os.path.basename(sys.argv[2]))
+    sys.exit(0)
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
 G = "gpurun_out"
@@ -51,29 +87,7 @@ if os.path.exists(f"{G}/launches_{tag}.csv"):
     shutil.copy(f"{G}/launches_{tag}.csv", f"profiles/{tag}_launches.csv")
 json.dump(b, open(f"profiles/{tag}_bench.json", "w"))
 
-raw = subprocess.run(["ncu", "-i", f"{G}/prof_{tag}.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-r = list(csv.reader(raw.splitlines())); h, units = r[0], r[1]
-keys = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread',
-        'launch__shared_mem_per_block_dynamic', 'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
-        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'smsp__thread_inst_executed_per_inst_executed.ratio',
-        'dram__bytes_read.sum', 'dram__bytes_write.sum', 'dram__throughput.avg.pct_of_peak_sustained_elapsed',
-        'l1tex__throughput.avg.pct_of_peak_sustained_active', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
-        'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed',
-        'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
-        'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active', 'l1tex__t_sector_pipe_lsu_mem_global_op_ld_hit_rate.pct',
-        'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum',
-        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
-        'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
-        'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
-        'smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio',
-        'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio', 'smsp__warps_eligible.avg.per_cycle_active']
-o2 = [f"# ncu --set full, {tag}", "",
-      "Raw report kept out of git; regenerate with the command in profiles/README.md. Values per launch (the last capture of each kernel).", ""]
-last = collections.OrderedDict((row[h.index('Kernel Name')], row) for row in r[2:])
-for row in last.values():
-    o2 += [f"## {row[h.index('Kernel Name')]}", "", "| metric | value | unit |", "|---|---:|---|"]
-    o2 += [f"| {k} | {row[h.index(k)]} | {units[h.index(k)]} |" for k in keys if k in h] + [""]
-open(f"profiles/{tag}_ncu_full_summary.md", "w").write("\n".join(o2))
+h, units, last = summarise(f"{G}/prof_{tag}.ncu-rep", f"profiles/{tag}_ncu_full_summary.md", tag)
 
 # counters bench.py needs, of the dominant kernel on bench.py's own workload
 samp = [row for name, row in last.items() if name.startswith("void cgb_sample_kernel<double, 0, 0>") or "cgb_sample_kernel<double, 0, 0>" in name]

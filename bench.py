@@ -603,10 +603,14 @@ def run_cuda(args):
         pm.dm_virial._tables.clear()
         pm._gas_tables.clear()
         h2d = 8 * (12 * pm.num_elements + 4)  # CDF + spline-fit inputs of both species
-        host_dm = pm.generate_dm_particles(n_glob, prng=i, shard=(rank, world), host=host_dm)
-        host_gas = pm.generate_gas_particles(n_glob, prng=i + 1, shard=(rank, world), host=host_gas)
+        # wait=False: the gas species' table preparation and first chunks overlap the tail of the
+        # dark-matter copies; both species are complete after the two wait() calls below
+        host_dm = pm.generate_dm_particles(n_glob, prng=i, shard=(rank, world), host=host_dm, wait=False)
+        host_gas = pm.generate_gas_particles(n_glob, prng=i + 1, shard=(rank, world), host=host_gas, wait=False)
         # device -> host read of the step's result: the moments (mean trials) of this step
         _ = host_dm.diagnostics["dm"].as_dict()["mean_trials"]
+        host_dm.wait()
+        host_gas.wait()
         return h2d, host_dm.d2h_bytes + host_gas.d2h_bytes
 
     e2e_steps = max(2, min(args.steps, 5))
@@ -733,7 +737,7 @@ def run_cuda(args):
         "value_note": "value counts DM (pos+vel) and gas (pos, zero vel) particles of one step; the DM-only rate is dm_particles_per_s",
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "roofline": e2e_roofline,
-                "what": "ClusterModel.generate_dm_particles + generate_gas_particles(host=True) from host tables: chunked generation, every chunk's D2H copy to pinned host memory overlapped with the next chunk's kernels; gas velocities (identically zero) are host-side zeros"},
+                "what": "ClusterModel.generate_dm_particles + generate_gas_particles(host=..., wait=False) + wait() from host tables: chunked generation, every chunk's D2H copy to pinned host memory overlapped with the next chunk's kernels and with the next species' table preparation; gas velocities (identically zero) are host-side zeros"},
         "configs": configs,
         # per step: cgb_sample_kernel + cgb_hard_kernel (deferred long-tail pass) + cgb_gas_smem_kernel
         "gpu_launches": 3 * args.steps,

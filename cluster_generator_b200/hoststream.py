@@ -86,7 +86,11 @@ class HostStreamer:
         self.drained = [torch.cuda.Event(), torch.cuda.Event()]
         self.bytes = 0
 
-    def run(self, launch):
+    def run(self, launch, wait=True):
+        """``wait=False``: do not make the compute stream wait for the copies -- the caller keeps
+        this streamer alive and calls :meth:`synchronize` (``ClusterParticles.wait``) before the
+        host arrays are read; kernels enqueued meanwhile (the next species' tables and chunks)
+        overlap the tail of these copies."""
         compute = torch.cuda.current_stream(self.dev)
         for c, a in enumerate(range(0, self.n, self.chunk)):
             b = min(a + self.chunk, self.n)
@@ -106,6 +110,11 @@ class HostStreamer:
                         dst[a:b].copy_(src[: b - a], non_blocking=True)
                     self.bytes += rows * (b - a) * src.element_size()
                 self.drained[s].record(self.copy_stream)
-        # the caller's stream sees the host buffers complete
-        compute.wait_stream(self.copy_stream)
+        if wait:
+            # the caller's stream sees the host buffers complete
+            compute.wait_stream(self.copy_stream)
         return self.host
+
+    def synchronize(self):
+        """Block the host until every copy issued by :meth:`run` has landed."""
+        self.copy_stream.synchronize()

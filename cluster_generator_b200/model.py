@@ -412,7 +412,7 @@ class ClusterModel:
         return self._gas_tables[key]
 
     def _generate_radial(self, ptype, num_particles, r_max, sub_sample, compute_potential, prng,
-                         dtype, rng, shard, host=False, chunk=None):
+                         dtype, rng, shard, host=False, chunk=None, wait=True):
         if "gas_mass" not in self.fields:
             raise RuntimeError("This ClusterModel contains no gas!")
         num_particles, sub_sample = int(num_particles), int(sub_sample)
@@ -472,12 +472,13 @@ class ClusterModel:
                 N.check(N.lib().cgb_sample_gas(N.ctypes.byref(a), N.ptr(stage.get("thermal_energy")),
                                                N.ptr(stage.get("density")), N.stream_ptr()))
 
-            hb = hs.run(launch) if n_loc > 0 else hs.host
+            hb = hs.run(launch, wait=wait) if n_loc > 0 else hs.host
             # the velocities are identically zero (model.py:829-831, 933-935): host-side zeros
             velh = getattr(host, "_host_vel", {}).get(ptype) if isinstance(host, ClusterParticles) else None
             if velh is None or velh.shape != (3, n_loc) or velh.dtype != dtype:
                 velh = torch.zeros((3, n_loc), dtype=dtype, pin_memory=True)
-            hs.copy_stream.synchronize()
+            if wait:
+                hs.copy_stream.synchronize()
             fields = OrderedDict()
             fields[ptype, "particle_position"] = hb.arrays["particle_position"].T
             if not tracer:
@@ -490,6 +491,8 @@ class ClusterModel:
                 fields[ptype, "particle_potential"] = hb.arrays["particle_potential"]
             out = ClusterParticles(ptype, fields)
             out._host_buffers, out._host_vel, out.d2h_bytes = {ptype: hb}, {ptype: velh}, hs.bytes
+            if not wait:
+                out._pending.append(hs)  # keeps the staging slots alive until the copies have left them
             return out
         pos = torch.empty((3, n_loc), dtype=dtype, device=dev)
         vel = torch.empty((3, n_loc), dtype=dtype, device=dev)
@@ -524,14 +527,15 @@ class ClusterModel:
 
     def generate_gas_particles(self, num_particles, r_max=None, sub_sample=1, compute_potential=False,
                                prng=None, *, dtype=torch.float64, rng="device", shard=None, host=False,
-                               chunk=None):
-        """Gas particles in hydrostatic equilibrium (model.py:838-947).  ``host``: see
+                               chunk=None, wait=True):
+        """Gas particles in hydrostatic equilibrium (model.py:838-947).  ``host``, ``wait``: see
         :meth:`VirialEquilibrium.generate_particles`."""
         return self._generate_radial("gas", num_particles, r_max, sub_sample, compute_potential, prng,
-                                     dtype, rng, shard, host, chunk)
+                                     dtype, rng, shard, host, chunk, wait)
 
     def generate_tracer_particles(self, num_particles, r_max=None, sub_sample=1, prng=None, *,
-                                  dtype=torch.float64, rng="device", shard=None, host=False, chunk=None):
+                                  dtype=torch.float64, rng="device", shard=None, host=False, chunk=None,
+                                  wait=True):
         """Tracer particles following the gas distribution (model.py:766-836)."""
         return self._generate_radial("tracer", num_particles, r_max, sub_sample, False, prng, dtype,
-                                     rng, shard, host, chunk)
+                                     rng, shard, host, chunk, wait)

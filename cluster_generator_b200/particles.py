@@ -107,6 +107,8 @@ def _to_device_planes(a, device) -> torch.Tensor:
 
 class ClusterParticles:
     def __init__(self, particle_types, fields, diagnostics=None):
+        #: host streamers whose device->host copies may still be in flight (``host=..., wait=False``)
+        self._pending = []
         self.particle_types = ensure_list(particle_types)
         self.fields = fields
         self.field_units = {k: FIELD_UNITS.get(k[1], "") for k in fields}
@@ -115,6 +117,25 @@ class ClusterParticles:
         self.passive_scalars = []
         #: per-ptype sampler diagnostics (moments from the kernel: trials/particle ...)
         self.diagnostics = diagnostics or {}
+
+    def wait(self):
+        """Block until the host arrays of a ``generate_*_particles(host=..., wait=False)`` call are
+        complete.  Any access to the fields (``particles[key]``, ``particles.fields``, every
+        method that reads them) does this by itself."""
+        for hs in self._pending:
+            hs.synchronize()
+        self._pending = []
+        return self
+
+    @property
+    def fields(self):
+        if self._pending:
+            self.wait()
+        return self._fields
+
+    @fields.setter
+    def fields(self, value):
+        self._fields = value
 
     def __getitem__(self, key):
         return self.fields[key]

@@ -376,6 +376,7 @@ class VirialEquilibrium:
         peer_moments=None,
         host=False,
         chunk=None,
+        wait=True,
     ):
         """
         Generate a set of dark matter or star particles in virial equilibrium
@@ -403,6 +404,9 @@ class VirialEquilibrium:
             pieces whose device->host copies overlap the next piece's kernels
             (:mod:`cluster_generator_b200.hoststream`); values are bit-identical to the
             device path.
+        wait : with ``host``: False returns while the last copies are still in flight, so the
+            next species' table preparation and first chunks overlap them; the arrays are
+            complete after ``particles.wait()`` (``particles[key]`` calls it).
         """
         num_particles = int(num_particles)
         sub_sample = int(sub_sample)
@@ -497,8 +501,9 @@ class VirialEquilibrium:
                 N.check(L.cgb_sample_particles(N.ctypes.byref(a), N.ptr(tabs.scratch), tabs.scratch.numel(),
                                                N.stream_ptr()))
 
-            hb = hs.run(launch) if n_loc > 0 else hs.host
-            hs.copy_stream.synchronize()
+            hb = hs.run(launch, wait=wait) if n_loc > 0 else hs.host
+            if wait:
+                hs.copy_stream.synchronize()
             fields = OrderedDict()
             fields[key, "particle_position"] = hb.arrays["particle_position"].T
             fields[key, "particle_velocity"] = hb.arrays["particle_velocity"].T
@@ -510,6 +515,8 @@ class VirialEquilibrium:
             out = ClusterParticles(key, fields, diag)
             out._host_buffers = {key: hb}
             out.d2h_bytes = hs.bytes
+            if not wait:
+                out._pending.append(hs)  # keeps the staging slots alive until the copies have left them
             return out
 
         if n_loc > 0 and sub_sample == 1:

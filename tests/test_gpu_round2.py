@@ -190,6 +190,20 @@ def test_host_streaming_is_bit_identical_to_the_device_path():
         d2 = pm.generate_dm_particles(n, prng=0, dtype=torch.float32)
     assert h2["dm", "particle_mass"].data_ptr() == h["dm", "particle_mass"].data_ptr()
     assert torch.equal(h2["dm", "particle_velocity"], d2["dm", "particle_velocity"].cpu())
+    # wait=False: the call returns with copies in flight, a second species is generated meanwhile,
+    # and the first access to the fields completes them
+    with _seeded(14):
+        ha = pm.generate_dm_particles(n, prng=0, host=True, chunk=65_536, wait=False)
+        ga = pm.generate_gas_particles(n, prng=0, host=True, chunk=65_536, wait=False)
+        dd = pm.generate_dm_particles(n, prng=0)
+        gd = pm.generate_gas_particles(n, prng=0)
+    assert len(ha._pending) == 1 and len(ga._pending) == 1
+    assert ha.wait() is ha and not ha._pending
+    for k in dd.fields:
+        assert torch.equal(ha[k], dd[k].cpu()), k
+    for k in gd.fields:   # no explicit wait: the field access does it
+        assert torch.equal(ga[k], gd[k].cpu()), k
+    assert not ga._pending
     # sub_sample > 1 and rng="numpy" take the copy-after path
     with _seeded(13):
         a = pm.generate_dm_particles(40_000, prng=3, sub_sample=4, host=True)

@@ -728,7 +728,7 @@ def run_cuda(args):
                    "parallelism": f"index-sharded x{world}",
                    "moments_reduce": {"peer": "fused into the sampler kernel over peer-mapped buffers (NVLink)",
                                       "nccl": "NCCL all_reduce per step", "local": "single GPU"}[mom_mode]},
-        "fE_build_ms": min(fe_ms), "fE_build_note": "bit-equal to scipy (FITPACK-exact spline fits)",
+        "fE_build_ms": min(fe_ms), "fE_build_note": "bit-equal to scipy (FITPACK-exact spline fits); host tables in, f(E) spline resident on the device (the host copy of df is made on demand)",
         "fE_build_shared_grid_ms": min(fe_shared_ms),
         "fE_build_shared_grid_note": "a further species of the same model (stars after dark matter): the Givens factorisation of the shared energy grid is re-used, bit-equal too",
         "fE_build_fast_ms": min(fe_fast_ms), "fE_build_fast_note": "PCR spline fits, f within 1e-11 of scipy",

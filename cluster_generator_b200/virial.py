@@ -220,7 +220,20 @@ class VirialEquilibrium:
         self.f = DeviceSpline(ft, fc)
         # g and QUADPACK's per-bin diagnostics stay on the device until somebody asks for them
         self._g_dev, self._last_dev, self._ier_dev = g, last, ier
-        self.df = unit_array(ff.cpu().numpy()[::-1].copy(), "Msun*Myr**3/kpc**6")
+        # ... and so does f(E) itself: the sampler reads the device spline; `df` / `ff` copy on demand
+        self._df, self._ff_dev = None, ff
+
+    @property
+    def df(self):
+        """f(E) in radius order (virial.py:68), a host array like the reference's; copied from the
+        device the first time it is asked for."""
+        if self._df is None and getattr(self, "_ff_dev", None) is not None:
+            self._df = unit_array(self._ff_dev.cpu().numpy()[::-1].copy(), "Msun*Myr**3/kpc**6")
+        return self._df
+
+    @df.setter
+    def df(self, value):
+        self._df, self._ff_dev = value, None
 
     @property
     def g(self):

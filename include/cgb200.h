@@ -125,7 +125,7 @@ int cgb_spline_eval(const double *d_t, const double *d_c, int n, const double *d
  * The quadrature is a decision-for-decision restatement of QUADPACK dqagse
  * (21-point Gauss-Kronrod, bisection, epsilon extrapolation, limit = 50).
  * fit_method: CGB_FIT_FITPACK makes g, ff and the f spline bit-equal to scipy's (the three
- * spline fits share one factorisation by fpcurf's own solve, ~0.85 ms in all); CGB_FIT_PCR is ~2.6x faster overall and
+ * spline fits share one factorisation by fpcurf's own solve, ~0.72 ms of kernels in all); CGB_FIT_PCR is ~2.6x faster overall and
  * within 1e-11 of it. */
 size_t cgb_eddington_workspace_bytes(int n);
 int cgb_eddington_df(const double *d_ee, const double *d_pden, int n, double epsabs, double epsrel,

@@ -187,6 +187,38 @@ def test_cluster_particles_container():
     assert allp.particle_types == ["dm"] and ("star", "particle_mass") not in allp
 
 
+def test_pending_host_copies_are_completed_by_any_field_access():
+    """generate_*_particles(host=..., wait=False) hands back particles whose device->host copies
+    may still be in flight; every path to the fields must complete them first."""
+    from cluster_generator_b200 import ClusterParticles
+
+    class FakeStreamer:
+        def __init__(self):
+            self.synced = 0
+
+        def synchronize(self):
+            self.synced += 1
+
+    def make():
+        n = 4
+        pos = torch.arange(3 * n, dtype=torch.float64).reshape(3, n)
+        p = ClusterParticles("dm", {("dm", "particle_position"): pos.T, ("dm", "particle_velocity"): (pos * 2).T,
+                                    ("dm", "particle_mass"): torch.ones(n, dtype=torch.float64)})
+        hs = FakeStreamer()
+        p._pending.append(hs)
+        return p, hs
+
+    for touch in (lambda p: p["dm", "particle_mass"], lambda p: p.fields, lambda p: p.wait(),
+                  lambda p: p + p, lambda p: p.add_offsets([1.0, 0.0, 0.0], [0.0, 0.0, 0.0]),
+                  lambda p: ("dm", "particle_mass") in p, lambda p: list(p.keys())):
+        p, hs = make()
+        assert hs.synced == 0          # constructing the container does not wait
+        touch(p)
+        assert hs.synced == 1 and p._pending == [], touch
+        touch(p)
+        assert hs.synced == 1          # and only once
+
+
 def test_radial_cut_and_black_hole():
     """particles.py:139-225 on CPU tensors."""
     from cluster_generator_b200 import ClusterParticles

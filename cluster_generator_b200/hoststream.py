@@ -9,6 +9,11 @@ chunk i+1's kernels.  One ``cudaMemcpyAsync`` per plane and chunk (both sides co
 nothing else on the copy stream.  Every particle is a pure function of (tables, seed, id),
 so the result is bit-identical to the one-shot device path.
 
+``generate_*_particles(..., host=..., wait=False)`` returns while the last copies are still in
+flight: the caller's next calls (another species' table preparation and first chunks) overlap
+them.  The returned ``ClusterParticles`` keeps the streamer -- and with it the staging slots the
+copies read from -- until ``wait()``, which any access to its fields calls.
+
 ``bind_host_to_gpu()`` pins the calling process to the CPU cores NVML reports as local to
 its GPU before any pinned memory is allocated: pinned pages are then taken from that
 socket's DRAM (first touch) and the copies of the 8 ranks of a box do not funnel through

@@ -5,7 +5,6 @@ import sys
 sys.path.insert(0, ".")
 import torch
 from tests.configs import product_model
-import cluster_generator_b200.virial as V
 
 name = sys.argv[1] if len(sys.argv) > 1 else "vikhlinin"
 n = int(float(sys.argv[2])) if len(sys.argv) > 2 else 10_000_000

@@ -13,7 +13,7 @@ outputs:
                             bench.py reads it for roofline.traffic / roofline.issue and flags
                             "stale" when cgb_sampler.cu has changed since the capture.
 """
-import collections, csv, hashlib, json, os, shutil, subprocess, sys
+import collections, csv, json, os, shutil, subprocess, sys
 
 KEYS = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread',
         'launch__shared_mem_per_block_dynamic', 'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',

@@ -1,6 +1,6 @@
 """Kernel-only timing of the fused sampler for one model (dev tool).
 usage: quick_bench.py [model] [n] ; env CGB200_LIB selects the library variant."""
-import sys, time
+import sys
 sys.path.insert(0, ".")
 import torch
 from tests.configs import product_model

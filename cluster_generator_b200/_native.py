@@ -79,6 +79,8 @@ SYMBOLS = [
     ("cgb_spline_fit_workspace_bytes", c_size_t, [c_int]),
     ("cgb_spline_fit", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     ("cgb_test_givens_cycles", c_int, [c_void_p]),
+    ("cgb_test_fpgivs", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    ("cgb_test_fpgivs_redo", c_int, [c_int, POINTER(c_int)]),
     ("cgb_bounds_check_enabled", c_int, []),
     ("cgb_test_bounds_check", c_int, [ctypes.c_longlong, ctypes.c_longlong]),
     ("cgb_test_div_by_rcp", c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),

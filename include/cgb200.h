@@ -98,6 +98,15 @@ int cgb_test_div_by_rcp(const double *d_x, const double *d_b, double *d_q, int64
 /* Profiling hook: clock64 ticks of the four phases (serial prologue, register-window run, serial
  * epilogue, back-substitution) of the last FITPACK-exact fit: [0..3] factorising, [4..7] re-using. */
 int cgb_test_givens_cycles(long long *host8);
+/* Test hooks of the factorising fit's rotations.  cgb_test_fpgivs: FITPACK's fpgivs on n operand
+ * pairs (piv != 0, ww > 0) in its branch-free form and with the plain operators; d_fast / d_plain
+ * receive (dd, cos, sin) per pair, d_flag the range test that sends the fit back to the plain
+ * operators -- tests assert the two agree bit for bit wherever the flag is 0.
+ * cgb_test_fpgivs_redo: *was_redone = whether a factorising fit since the last call repeated its
+ * triangularisation with the plain operators; `force` != 0 makes the following fits do so. */
+int cgb_test_fpgivs(const double *d_piv, const double *d_ww, double *d_fast, double *d_plain, int *d_flag,
+                    int64_t n, void *stream);
+int cgb_test_fpgivs_redo(int force, int *was_redone);
 
 /* Bounds-checked build (`make -C cluster_generator_b200/csrc checked` -> libcgb200_checked.so,
  * -DCGB_BOUNDS_CHECK): every table, tile-buffer and output index of the kernels is a device-side

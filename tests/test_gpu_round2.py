@@ -147,6 +147,72 @@ def test_back_substitution_quotient_is_the_ieee_quotient():
     assert torch.equal(q, x / b)
 
 
+def test_branch_free_fpgivs_equals_the_plain_operators_and_the_fit_survives_a_redo():
+    """The factorising fit computes FITPACK's rotations with the compiler's own division / sqrt /
+    reciprocal sequences minus their special-operand branches.  (dd, cos, sin) must equal the
+    plain-operator results bit for bit on every operand pair its range test lets through, the
+    test must flag what it cannot vouch for, and a fit forced back to the plain operators must
+    give the same coefficients."""
+    import ctypes
+
+    from scipy.interpolate import InterpolatedUnivariateSpline as IUS
+
+    from cluster_generator_b200 import _native as N
+    from cluster_generator_b200.virial import DeviceSpline
+
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(9)
+    n = 1 << 22
+
+    def operands(lo, hi):
+        def one():
+            m = torch.rand(n, generator=g, device=dev, dtype=torch.float64) + 1.0
+            return m * torch.exp2(torch.randint(lo, hi + 1, (n,), generator=g, device=dev).double())
+        sign = torch.randint(0, 2, (n,), generator=g, device=dev).double() * 2 - 1
+        return one() * sign, one()
+
+    def run(piv, ww):
+        m = piv.numel()
+        fast = torch.empty(3 * m, dtype=torch.float64, device=dev)
+        plain = torch.empty_like(fast)
+        flag = torch.empty(m, dtype=torch.int32, device=dev)
+        N.check(N.lib().cgb_test_fpgivs(N.ptr(piv), N.ptr(ww), N.ptr(fast), N.ptr(plain), N.ptr(flag), m,
+                                        N.stream_ptr()))
+        return fast.view(torch.int64), plain.view(torch.int64), flag
+
+    # the whole admitted range, near-equal magnitudes, and the extreme ratios inside it
+    for lo, hi in ((-299, 298), (-3, 3), (0, 0)):
+        fast, plain, flag = run(*operands(lo, hi))
+        assert int(flag.sum()) == 0
+        assert torch.equal(fast, plain), (lo, hi)
+    piv, ww = operands(-299, -290)
+    fast, plain, flag = run(piv, ww * 2.0 ** 588)
+    assert int(flag.sum()) == 0 and torch.equal(fast, plain)
+    fast, plain, flag = run(piv * 2.0 ** 588, ww)
+    assert int(flag.sum()) == 0 and torch.equal(fast, plain)
+    # outside: flagged (whatever the fast form returns there is discarded by the fit)
+    bad_p = torch.tensor([1e-300, 1.0, 1e300, float("inf"), float("nan"), 0.0, 1e-310, 1.0], dtype=torch.float64, device=dev)
+    bad_w = torch.tensor([1.0, 1e-300, 1.0, 1.0, 1.0, 1.0, 1.0, 1e95], dtype=torch.float64, device=dev)
+    _, _, flag = run(bad_p, bad_w)
+    assert flag.tolist() == [1] * 8
+
+    # a fit sent back to the plain operators
+    om = oracle_model("vikhlinin")
+    x, y = -om["gravitational_potential"][::-1], om["dark_matter_density"][::-1]
+    was = ctypes.c_int(0)
+    N.check(N.lib().cgb_test_fpgivs_redo(0, ctypes.byref(was)))
+    c0 = DeviceSpline.fit(x, y, method="fitpack").get_coeffs()
+    N.check(N.lib().cgb_test_fpgivs_redo(1, ctypes.byref(was)))
+    assert was.value == 0                       # the normal fit never needed it
+    try:
+        c1 = DeviceSpline.fit(x, y, method="fitpack").get_coeffs()
+    finally:
+        N.check(N.lib().cgb_test_fpgivs_redo(0, ctypes.byref(was)))
+    assert was.value == 1                       # the forced one did
+    np.testing.assert_array_equal(c0, c1)
+    np.testing.assert_array_equal(c0, IUS(x, y).get_coeffs())
+
+
 def test_fitpack_exact_fit_small_and_odd_sizes_bit_equal():
     """The two-lane wavefront factorisation at full, odd and minimal sizes equals scipy's
     FITPACK coefficients bit for bit (the factor re-use path is covered by the f(E) tests)."""

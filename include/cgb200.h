@@ -78,7 +78,7 @@ int cgb_measure_ffma_tflops(int iters, double *tflops, void *stream);
  * not inspect the data: x must be strictly increasing (scipy raises ValueError for that at
  * virial.py:45); the Python wrapper checks it on the host, where the tables come from.
  * method: CGB_FIT_FITPACK = fpcurf's own Givens-rotation solve, coefficients bit-equal to
- * scipy's (a serial dependency chain run by one thread from registers, ~0.45 ms for n = 1000,
+ * scipy's (a serial dependency chain run by one thread from registers, ~0.26 ms for n = 1000,
  * ~0.08 ms when the factorisation is re-used; used by the f(E) build, whose quadrature
  * decisions and spline derivative amplify coefficient noise); CGB_FIT_PCR = parallel cyclic
  * reduction of the same collocation system, ~20 us, coefficients within 1e-13 of FITPACK's. */
@@ -134,7 +134,7 @@ int cgb_spline_eval(const double *d_t, const double *d_c, int n, const double *d
  * The quadrature is a decision-for-decision restatement of QUADPACK dqagse
  * (21-point Gauss-Kronrod, bisection, epsilon extrapolation, limit = 50).
  * fit_method: CGB_FIT_FITPACK makes g, ff and the f spline bit-equal to scipy's (the three
- * spline fits share one factorisation by fpcurf's own solve, ~0.72 ms of kernels in all); CGB_FIT_PCR is ~2.6x faster overall and
+ * spline fits share one factorisation by fpcurf's own solve, ~0.55 ms of kernels in all); CGB_FIT_PCR is ~2.2x faster overall and
  * within 1e-11 of it. */
 size_t cgb_eddington_workspace_bytes(int n);
 int cgb_eddington_df(const double *d_ee, const double *d_pden, int n, double epsabs, double epsrel,

@@ -214,7 +214,7 @@ def test_branch_free_fpgivs_equals_the_plain_operators_and_the_fit_survives_a_re
 
 
 def test_fitpack_exact_fit_small_and_odd_sizes_bit_equal():
-    """The two-lane wavefront factorisation at full, odd and minimal sizes equals scipy's
+    """The register-window factorisation at full, odd and minimal sizes equals scipy's
     FITPACK coefficients bit for bit (the factor re-use path is covered by the f(E) tests)."""
     from scipy.interpolate import InterpolatedUnivariateSpline as IUS
 

@@ -21,11 +21,13 @@ for line in sass.splitlines():
         kernels[cur][m.group(1)] += 1
 demangle = subprocess.run(["cu++filt"] + list(kernels), capture_output=True, text=True).stdout.splitlines()
 names = dict(zip(kernels, demangle if len(demangle) == len(kernels) else list(kernels)))
-want = ("cgb_sample_kernel<double, 0, false>", "cgb_gas_smem_kernel<double, false>", "cgb_gas_kernel<double, false>",
-        "cgb_hard_kernel<double, 0, false>", "cgb_givens_kernel<true>", "cgb_givens_kernel<false>", "cgb_eddington_g_kernel",
+# cu++filt prints template arguments as "(int)0, (bool)1": compare without the casts
+names = {k: re.sub(r"\((?:int|bool)\)", "", v) for k, v in names.items()}
+want = ("cgb_sample_kernel<double, 0, 0>", "cgb_gas_smem_kernel<double, 0>", "cgb_gas_kernel<double, 0>",
+        "cgb_hard_kernel<double, 0, 0>", "cgb_givens_kernel<1>", "cgb_givens_kernel<0>", "cgb_eddington_g_kernel",
         "cgb_qags_replay_kernel", "cgb_screen_audit_kernel")
 key_ops = ("UBLKCP", "SYNCS", "IMAD.WIDE.U32", "LOP3.LUT", "DFMA", "DMUL", "DADD", "FFMA", "FMUL", "MUFU", "LDS", "LDG", "STG",
-           "SHFL", "VOTE", "ATOM", "RED", "BAR", "WARPSYNC")
+           "SHFL", "VOTE", "ATOM", "RED", "BAR", "WARPSYNC", "S2UR", "BRA", "CALL")
 out = [f"# SASS opcode histogram of the shipped library, {tag} (`cuobjdump -sass cluster_generator_b200/lib/libcgb200.so`, sm_100a)", "",
        "Static instruction counts per kernel. `UBLKCP` = cp.async.bulk (TMA bulk copy global -> shared), `SYNCS` = mbarrier",
        "operations (init / arrive.expect_tx / try_wait); `IMAD.WIDE.U32` = the 32x32 -> 64-bit products of Philox4x32-10.", ""]

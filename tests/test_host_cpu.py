@@ -59,6 +59,39 @@ def test_ctypes_structs_match_the_c_header_layout():
     assert got == want
 
 
+def test_shipped_kernels_carry_the_tma_bulk_copy_and_the_philox_products():
+    """The SASS of the built library (what profiles/r02_sass_opcodes.md tabulates): the sampler and
+    the gas fast path stage their tables with a TMA bulk copy (UBLKCP) completed on an mbarrier
+    (SYNCS), Philox is IMAD.WIDE.U32 products, and the two hot loops do not re-derive the
+    shared-memory window base (S2UR SR_CgaCtaId) at every access."""
+    import shutil
+
+    if shutil.which("cuobjdump") is None or shutil.which("cu++filt") is None:
+        pytest.skip("CUDA binary utilities are not on PATH")
+    so = os.path.join(ROOT, "cluster_generator_b200", "lib", "libcgb200.so")
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, check=True).stdout
+    kernels, cur = {}, None
+    for line in sass.splitlines():
+        m = re.match(r"\s+Function : (\S+)", line)
+        if m:
+            cur = kernels.setdefault(m.group(1), [])
+        elif cur is not None and re.match(r"\s+/\*[0-9a-f]{4,}\*/", line):
+            cur.append(line)
+    names = subprocess.run(["cu++filt"] + list(kernels), capture_output=True, text=True, check=True).stdout.splitlines()
+    by_name = {re.sub(r"\((?:int|bool)\)", "", n): body for n, body in zip(names, kernels.values())}
+
+    def count(kernel, needle):
+        (body,) = [b for n, b in by_name.items() if kernel in n]
+        return sum(needle in line for line in body)
+
+    samp, gas = "cgb_sample_kernel<double, 0, 0>", "cgb_gas_smem_kernel<double, 0>"
+    for k in (samp, gas):
+        assert count(k, "UBLKCP") >= 1 and count(k, "SYNCS") >= 2, k
+    assert count(samp, "IMAD.WIDE.U32") >= 150      # 2 per round x 10 rounds x the inlined Philox calls
+    assert count(samp, "SR_CgaCtaId") <= 10 and count(gas, "SR_CgaCtaId") <= 2
+    assert count(samp, "DFMA") > 0 and count(gas, "STG.E.128") >= 1
+
+
 def test_no_cpu_fallback():
     """Without a GPU the product path must fail loudly, not route through the oracle."""
     if torch.cuda.is_available():
